@@ -1,0 +1,64 @@
+// Library context: one CUDA device, one stream, grow-only device scratch buffers.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdio>
+#include <mutex>
+#include <string>
+
+#include "../../include/curdle_b200.h"
+
+namespace cdl {
+constexpr size_t kMsmMaxSmem = 220 * 1024;          // dynamic shared memory opt-in for k_msm_small
+constexpr size_t kMsmMaxTerms = kMsmMaxSmem / 36;   // 36 B of staging per term
+
+__global__ void k_iota(uint32_t* out, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = i;
+}
+}  // namespace cdl
+
+struct cdl_ctx {
+  int device = 0;
+  int sm_count = 0;
+  int clock_khz = 0;
+  std::string name;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::mutex mu;
+  std::string err;
+  static constexpr int kSlots = 8;
+  void* slot[kSlots] = {};
+  size_t cap[kSlots] = {};
+
+  // grow-only scratch buffer `i` of at least `bytes`
+  void* buf(int i, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    if (cap[i] >= bytes) return slot[i];
+    if (slot[i]) { cudaStreamSynchronize(stream); cudaFree(slot[i]); slot[i] = nullptr; cap[i] = 0; }
+    size_t want = bytes + bytes / 2;
+    if (cudaMalloc(&slot[i], want) != cudaSuccess) { slot[i] = nullptr; return nullptr; }
+    cap[i] = want;
+    return slot[i];
+  }
+  void free_all() {
+    for (int i = 0; i < kSlots; i++) if (slot[i]) { cudaFree(slot[i]); slot[i] = nullptr; cap[i] = 0; }
+  }
+  int32_t fail(int32_t code, const char* fmt, ...) {
+    char tmp[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(tmp, sizeof tmp, fmt, ap);
+    va_end(ap);
+    err = tmp;
+    return code;
+  }
+};
+
+#define CDL_CUDA(ctx, call)                                                                   \
+  do {                                                                                        \
+    cudaError_t e__ = (call);                                                                 \
+    if (e__ != cudaSuccess)                                                                   \
+      return (ctx)->fail(CDL_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                         __FILE__, __LINE__);                                                 \
+  } while (0)

@@ -1,0 +1,226 @@
+// Montgomery arithmetic on N 32-bit limbs (N even), generic over the modulus.
+//
+// Elements are plain little-endian limb arrays in Montgomery form, always fully
+// reduced to [0, p).  This is byte-for-byte gnark-crypto's fp.Element /
+// fr.Element memory layout ([6]uint64 / [4]uint64 little-endian, Montgomery,
+// R = 2^(32N)), so host buffers cross the C ABI without conversion
+// (SURVEY.md §8 header).
+//
+// Multiplication is a CIOS product with the partial products split into an
+// "even" and an "odd" accumulator so that every a[j]*b_i lands on an aligned
+// 64-bit column pair: each row is N/2 + N/2 IMAD.WIDE for the product, the same
+// again for the reduction, plus one low multiply for the quotient digit —
+// 2N^2 + N wide multiply-adds per product (300 for the 381-bit field), which is
+// the unit the integer-pipe roofline is stated in.
+#pragma once
+#include "carry.cuh"
+
+namespace cdl {
+
+template <class F>
+struct Mont {
+  static constexpr int N = F::N;
+  // 16-byte aligned in device code so that loads/stores vectorise to 128 bit
+  // (cudaMalloc'ed arrays of 32/48/96/144/192-byte elements keep that alignment).
+#if defined(__CUDACC__)
+  struct alignas(16) El { uint32_t v[N]; };
+#else
+  struct El { uint32_t v[N]; };
+#endif
+
+  // acc[0..N) = a[j]*bi for j = 0,2,4,.. (64-bit products on aligned pairs)
+  static CDL_HD void mul_n(uint32_t* acc, const uint32_t* a, uint32_t bi) {
+#pragma unroll
+    for (int j = 0; j < N; j += 2) {
+      acc[j] = mul_lo(a[j], bi);
+      acc[j + 1] = mul_hi(a[j], bi);
+    }
+  }
+
+  // acc[0..N) += a[j]*bi for j = 0,2,4,.. ; returns with the carry-out in cc.
+  static CDL_HD void cmad_n(CC& cc, uint32_t* acc, const uint32_t* a, uint32_t bi) {
+    acc[0] = mad_lo_cc(cc, a[0], bi, acc[0]);
+    acc[1] = madc_hi_cc(cc, a[0], bi, acc[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+      acc[j] = madc_lo_cc(cc, a[j], bi, acc[j]);
+      acc[j + 1] = madc_hi_cc(cc, a[j], bi, acc[j + 1]);
+    }
+  }
+
+  // Same with the modulus as multiplicand (limbs start .. start+N step 2).
+  template <int START>
+  static CDL_HD void cmad_mod(CC& cc, uint32_t* acc, uint32_t mi) {
+    acc[0] = mad_lo_cc(cc, F::mod(START), mi, acc[0]);
+    acc[1] = madc_hi_cc(cc, F::mod(START), mi, acc[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+      acc[j] = madc_lo_cc(cc, F::mod(START + j), mi, acc[j]);
+      acc[j + 1] = madc_hi_cc(cc, F::mod(START + j), mi, acc[j + 1]);
+    }
+  }
+
+  // odd[] >>= 64 bits while accumulating a[j]*bi (j = 0,2,..) with carry-in.
+  static CDL_HD void madc_n_rshift(CC& cc, uint32_t* odd, const uint32_t* a, uint32_t bi) {
+#pragma unroll
+    for (int j = 0; j < N - 2; j += 2) {
+      odd[j] = madc_lo_cc(cc, a[j], bi, odd[j + 2]);
+      odd[j + 1] = madc_hi_cc(cc, a[j], bi, odd[j + 3]);
+    }
+    odd[N - 2] = madc_lo_cc(cc, a[N - 2], bi, 0);
+    odd[N - 1] = madc_hi(cc, a[N - 2], bi, 0);
+  }
+
+  // One CIOS row: T = (T >> 32) + a*bi, then T += m*p with m chosen so that the
+  // low word cancels.  T = even + (odd << 32).
+  static CDL_HD void row(uint32_t* even, uint32_t* odd, const uint32_t* a, uint32_t bi, bool first) {
+    CC cc;
+    if (first) {
+      mul_n(odd, a + 1, bi);
+      mul_n(even, a, bi);
+    } else {
+      even[0] = add_cc(cc, even[0], odd[1]);
+      madc_n_rshift(cc, odd, a + 1, bi);
+      cmad_n(cc, even, a, bi);
+      odd[N - 1] = addc(cc, odd[N - 1], 0);
+    }
+    uint32_t mi = even[0] * F::M0;
+    cmad_mod<1>(cc, odd, mi);
+    cmad_mod<0>(cc, even, mi);
+    odd[N - 1] = addc(cc, odd[N - 1], 0);
+  }
+
+  // r = r - p if r >= p
+  static CDL_HD void final_sub(uint32_t* r) {
+    uint32_t t[N];
+    CC cc;
+    t[0] = sub_cc(cc, r[0], F::mod(0));
+#pragma unroll
+    for (int i = 1; i < N; i++) t[i] = subc_cc(cc, r[i], F::mod(i));
+    uint32_t borrow = subc(cc, 0, 0);  // 0 - 0 - CF : 0 or 0xffffffff
+#pragma unroll
+    for (int i = 0; i < N; i++) r[i] = borrow ? r[i] : t[i];
+  }
+
+  static CDL_HD void mul(El& r, const El& a, const El& b) {
+    uint32_t even[N], odd[N];
+#pragma unroll
+    for (int i = 0; i < N; i += 2) {
+      row(even, odd, a.v, b.v[i], i == 0);
+      row(odd, even, a.v, b.v[i + 1], false);
+    }
+    CC cc;
+    even[0] = add_cc(cc, even[0], odd[1]);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) even[i] = addc_cc(cc, even[i], odd[i + 1]);
+    even[N - 1] = addc(cc, even[N - 1], 0);
+    final_sub(even);
+#pragma unroll
+    for (int i = 0; i < N; i++) r.v[i] = even[i];
+  }
+
+  static CDL_HD void sqr(El& r, const El& a) { mul(r, a, a); }
+
+  static CDL_HD void add(El& r, const El& a, const El& b) {
+    uint32_t t[N];
+    CC cc;
+    t[0] = add_cc(cc, a.v[0], b.v[0]);
+#pragma unroll
+    for (int i = 1; i < N; i++) t[i] = addc_cc(cc, a.v[i], b.v[i]);
+    final_sub(t);  // moduli here leave >= 1 spare top bit: no carry out of limb N-1
+#pragma unroll
+    for (int i = 0; i < N; i++) r.v[i] = t[i];
+  }
+
+  static CDL_HD void sub(El& r, const El& a, const El& b) {
+    uint32_t t[N];
+    CC cc;
+    t[0] = sub_cc(cc, a.v[0], b.v[0]);
+#pragma unroll
+    for (int i = 1; i < N; i++) t[i] = subc_cc(cc, a.v[i], b.v[i]);
+    uint32_t borrow = subc(cc, 0, 0);
+    CC c2;
+    t[0] = add_cc(c2, t[0], borrow & F::mod(0));
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) t[i] = addc_cc(c2, t[i], borrow & F::mod(i));
+    t[N - 1] = addc(c2, t[N - 1], borrow & F::mod(N - 1));
+#pragma unroll
+    for (int i = 0; i < N; i++) r.v[i] = t[i];
+  }
+
+  static CDL_HD void dbl(El& r, const El& a) { add(r, a, a); }
+
+  static CDL_HD bool is_zero(const El& a) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) o |= a.v[i];
+    return o == 0;
+  }
+
+  static CDL_HD void neg(El& r, const El& a) {
+    uint32_t t[N];
+    CC cc;
+    t[0] = sub_cc(cc, F::mod(0), a.v[0]);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) t[i] = subc_cc(cc, F::mod(i), a.v[i]);
+    t[N - 1] = subc(cc, F::mod(N - 1), a.v[N - 1]);
+    bool z = is_zero(a);
+#pragma unroll
+    for (int i = 0; i < N; i++) r.v[i] = z ? 0u : t[i];
+  }
+
+  static CDL_HD bool eq(const El& a, const El& b) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) o |= a.v[i] ^ b.v[i];
+    return o == 0;
+  }
+
+  static CDL_HD void set_zero(El& r) {
+#pragma unroll
+    for (int i = 0; i < N; i++) r.v[i] = 0;
+  }
+
+  static CDL_HD void set_one(El& r) {
+#pragma unroll
+    for (int i = 0; i < N; i++) r.v[i] = F::one(i);
+  }
+
+  static CDL_HD void cmov(El& r, const El& a, bool c) {
+#pragma unroll
+    for (int i = 0; i < N; i++) r.v[i] = c ? a.v[i] : r.v[i];
+  }
+
+  // Montgomery form -> canonical integer limbs (one reduction pass: a * 1).
+  static CDL_HD void from_mont(El& r, const El& a) {
+    El one_raw;
+    set_zero(one_raw);
+    one_raw.v[0] = 1;
+    mul(r, a, one_raw);
+  }
+
+  static CDL_HD void to_mont(El& r, const El& a) {
+    El r2;
+#pragma unroll
+    for (int i = 0; i < N; i++) r2.v[i] = F::r2(i);
+    mul(r, a, r2);
+  }
+
+  // r = a^e, e given as NE little-endian 32-bit words (public exponent).
+  // 4-bit fixed window; a == 0 gives 0 for e != 0.
+  template <int NE>
+  static CDL_HD void pow_words(El& r, const El& a, const uint32_t* e) {
+    El tab[16];
+    set_one(tab[0]);
+    tab[1] = a;
+    for (int i = 2; i < 16; i++) mul(tab[i], tab[i - 1], a);
+    set_one(r);
+    for (int w = NE * 8 - 1; w >= 0; w--) {
+      sqr(r, r); sqr(r, r); sqr(r, r); sqr(r, r);
+      uint32_t d = (e[w >> 3] >> ((w & 7) * 4)) & 15;
+      mul(r, r, tab[d]);  // public exponent: data-independent index (local memory on device)
+    }
+  }
+};
+
+}  // namespace cdl

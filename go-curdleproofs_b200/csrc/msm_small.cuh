@@ -1,0 +1,182 @@
+// Batched small-MSM kernel: one CTA per independent MSM, one thread per bucket.
+//
+// Replaces (*G1Jac).MultiExp at every size Prove/Verify produce (1 .. 5*ell+8
+// terms; SURVEY.md §8a rows a1,a3-a6,a8,a10-a15), many MSMs per launch (the 4/6
+// MSMs of an IPA / SameMSM round, times the number of proofs in a batch).
+//
+// Signed 4-bit windows, W = 64 windows x 8 buckets = 512 threads.  Phases:
+//   1. recode   : scalars Montgomery -> canonical, k -> min(k, r-k) with the
+//                 point negated, k' = k + 0x0888..8 so that window digits are
+//                 ((k' >> 4w) & 15) - 8 with no carry chain at lookup time;
+//                 k' (32 B/term) is staged in shared memory.
+//   2. accumulate: thread (w, d) walks the terms, adds every point whose digit
+//                 in window w is +-d into its private XYZZ bucket (mixed add).
+//                 Lanes search for their next term independently (cheap) and
+//                 meet for the field arithmetic, so lanes are busy on different
+//                 points at once.
+//   3. reduce   : sum_d d*B_d per window as suffix scan + butterfly over the 8
+//                 lanes of a window with warp shuffles (6 adds instead of 16).
+//   4. combine  : binary tree over windows, level L doubles the upper operand
+//                 4*2^L times (252 doublings on the critical path, 6 adds).
+//   5. normalise: one inversion, affine result (+ optional compressed bytes).
+#pragma once
+#include "kernels.cuh"
+
+namespace cdl {
+
+constexpr int kMsmC = 4;
+constexpr int kMsmBuckets = 8;     // 2^(c-1)
+constexpr int kMsmWindows = 64;    // 63 signed windows (bits 0..251) + top raw window
+constexpr int kMsmThreads = kMsmBuckets * kMsmWindows;
+
+struct MsmTask {
+  uint32_t term_off;   // first term in idx[] / scalars[]
+  uint32_t term_cnt;
+};
+
+// 0x0888...8: 2^(c-1) in each of the 63 signed windows (bits 0..251)
+__device__ __forceinline__ uint32_t msm_bias_word(int i) { return i == 7 ? 0x08888888u : 0x88888888u; }
+
+// canonical k (8 words) -> biased k' and sign.  k < r.
+__device__ __forceinline__ bool msm_recode(uint32_t* kp, const Fr& k) {
+  // neg = r - k
+  uint32_t ng[8];
+  CC cc;
+  ng[0] = sub_cc(cc, FR_MOD_D[0], k.v[0]);
+#pragma unroll
+  for (int i = 1; i < 7; i++) ng[i] = subc_cc(cc, FR_MOD_D[i], k.v[i]);
+  ng[7] = subc(cc, FR_MOD_D[7], k.v[7]);
+  // use the negative when k > r - k  <=>  (r-k) - k borrows
+  CC c2;
+  (void)sub_cc(c2, ng[0], k.v[0]);
+#pragma unroll
+  for (int i = 1; i < 8; i++) (void)subc_cc(c2, ng[i], k.v[i]);
+  bool neg = subc(c2, 0, 0) != 0;
+  uint32_t m[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) m[i] = neg ? ng[i] : k.v[i];
+  CC c3;
+  kp[0] = add_cc(c3, m[0], msm_bias_word(0));
+#pragma unroll
+  for (int i = 1; i < 7; i++) kp[i] = addc_cc(c3, m[i], msm_bias_word(i));
+  kp[7] = addc(c3, m[7], msm_bias_word(7));
+  return neg;
+}
+
+__device__ __forceinline__ int msm_digit(const uint32_t* kp, int w) {
+  int nib = (int)((kp[w >> 3] >> ((w & 7) * 4)) & 15u);
+  return w == kMsmWindows - 1 ? nib : nib - 8;
+}
+
+__device__ __forceinline__ void xyzz_shfl_down(G1Xyzz& r, const G1Xyzz& p, int delta, int width) {
+  const uint32_t* s = reinterpret_cast<const uint32_t*>(&p);
+  uint32_t* d = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+  for (int i = 0; i < 48; i++) d[i] = __shfl_down_sync(0xffffffffu, s[i], delta, width);
+}
+
+// points: pool of affine points; idx[t] selects the base of term t (bit 31:
+// negate).  scalars[t]: gnark Montgomery fr.Element.  out_aff[j] / out_c48[j]:
+// result of task j (either pointer may be null).
+__global__ void __launch_bounds__(kMsmThreads, 1)
+k_msm_small(const G1Affine* __restrict__ points, const uint32_t* __restrict__ idx,
+            const Fr* __restrict__ scalars, const MsmTask* __restrict__ tasks,
+            G1Affine* __restrict__ out_aff, uint8_t* __restrict__ out_c48) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const MsmTask task = tasks[blockIdx.x];
+  const int T = (int)task.term_cnt;
+  const int tid = threadIdx.x;
+  // layout: kp[T][8] words, then pidx[T] words, then the combine scratch
+  uint32_t* kp = reinterpret_cast<uint32_t*>(smem_raw);
+  uint32_t* pidx = kp + (size_t)T * 8;
+
+  // ---- phase 1: recode
+  for (int t = tid; t < T; t += kMsmThreads) {
+    Fr km = scalars[task.term_off + t], k;
+    FrM::from_mont(k, km);
+    uint32_t tmp[8];
+    bool neg = msm_recode(tmp, k);
+#pragma unroll
+    for (int i = 0; i < 8; i++) kp[t * 8 + i] = tmp[i];
+    pidx[t] = idx[task.term_off + t] ^ (neg ? 0x80000000u : 0u);
+  }
+  __syncthreads();
+
+  // ---- phase 2: bucket accumulation
+  const int w = tid >> 3;
+  const int mybucket = (tid & 7) + 1;
+  G1Xyzz acc;
+  xyzz_set_inf(acc);
+  int t = 0;
+  while (true) {
+    int found = -1;
+    int sgn = 0;
+    while (t < T) {
+      int d = msm_digit(kp + t * 8, w);
+      int a = d < 0 ? -d : d;
+      if (a == mybucket) { found = t; sgn = d; t++; break; }
+      t++;
+    }
+    if (!__any_sync(0xffffffffu, found >= 0)) break;
+    if (found >= 0) {
+      uint32_t pi = pidx[found];
+      G1Affine q = points[pi & 0x7fffffffu];
+      bool neg = ((pi >> 31) != 0) != (sgn < 0);
+      if (neg) FpM::neg(q.y, q.y);
+      xyzz_add_mixed(acc, acc, q);
+    }
+  }
+
+  // ---- phase 3: window sum S_w = sum_d d * B_d over the 8 lanes of the window
+  G1Xyzz other;
+#pragma unroll
+  for (int off = 1; off < kMsmBuckets; off <<= 1) {  // suffix sums R_d = sum_{j>=d} B_j
+    xyzz_shfl_down(other, acc, off, kMsmBuckets);
+    if ((tid & 7) + off < kMsmBuckets) xyzz_add(acc, acc, other);
+  }
+#pragma unroll
+  for (int off = kMsmBuckets / 2; off >= 1; off >>= 1) {  // S_w = sum_d R_d
+    xyzz_shfl_down(other, acc, off, kMsmBuckets);
+    if ((tid & 7) < off) xyzz_add(acc, acc, other);
+  }
+
+  // ---- phase 4: combine windows (Jacobian: cheaper doublings)
+  __syncthreads();  // kp / pidx are dead from here on; reuse shared memory
+  G1Jac* win = reinterpret_cast<G1Jac*>(smem_raw);
+  if ((tid & 7) == 0) {
+    G1Jac j;
+    xyzz_to_jac(j, acc);
+    win[w] = j;
+  }
+  __syncthreads();
+  for (int level = 0, active = kMsmWindows / 2; active >= 1; level++, active >>= 1) {
+    G1Jac lo, hi;
+    if (tid < active) {
+      lo = win[2 * tid];
+      hi = win[2 * tid + 1];
+      int nd = kMsmC << level;
+      for (int i = 0; i < nd; i++) jac_dbl(hi, hi);
+      jac_add(lo, lo, hi);
+    }
+    __syncthreads();
+    if (tid < active) win[tid] = lo;
+    __syncthreads();
+  }
+
+  // ---- phase 5: normalise + store
+  if (tid == 0) {
+    G1Affine a;
+    jac_to_affine(a, win[0]);
+    if (out_aff) out_aff[blockIdx.x] = a;
+    if (out_c48) g1_compress_dev(out_c48 + 48 * (size_t)blockIdx.x, a);
+  }
+}
+
+// shared memory bytes for the largest task of a launch
+inline size_t msm_small_smem_bytes(size_t max_terms) {
+  size_t a = max_terms * 36;                       // kp + pidx
+  size_t b = (size_t)kMsmWindows * sizeof(G1Jac);  // combine scratch
+  return a > b ? a : b;
+}
+
+}  // namespace cdl

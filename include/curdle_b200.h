@@ -1,0 +1,126 @@
+/* curdle_b200 — C ABI of the B200-native BLS12-381 G1 hot path underneath
+ * jsign/go-curdleproofs.
+ *
+ * The reference has no FFI/plugin interface: its hot path is the set of
+ * gnark-crypto v0.11.0 methods it calls.  Each entry point
+ * below names the reference call sites (file:line under /root/reference) whose
+ * gnark call it replaces; INTEGRATION.md shows the cgo stubs that bind them.
+ *
+ * Conventions
+ *  - plain C, `extern "C"`, pointers + sizes only; no torch / CUDA types.
+ *  - memory layouts are gnark-crypto's, so Go slices cross without copies on
+ *    the Go side (`unsafe.Pointer(&s[0])`):
+ *      fp.Element  = 6 x uint64 little-endian limbs, Montgomery (R = 2^384)   48 B
+ *      fr.Element  = 4 x uint64 little-endian limbs, Montgomery (R = 2^256)   32 B
+ *      G1Affine    = {X, Y}      96 B, point at infinity == (0, 0)
+ *      G1Jac       = {X, Y, Z}  144 B, point at infinity == Z = 0
+ *  - every function returns CDL_OK (0) or a negative cdl_status;
+ *    cdl_last_error(ctx) gives a human-readable message for the calling thread's
+ *    last failure on that context.
+ *  - host-pointer entry points copy in/out and retain nothing after return (cgo
+ *    pointer rule).  A context is bound to one CUDA device and is safe to call
+ *    from many OS threads (calls serialise on an internal mutex; use one context
+ *    per thread or the *_batch entry points for concurrency).
+ *  - there is NO CPU fallback: without a CUDA device cdl_create fails with
+ *    CDL_ERR_NO_DEVICE.
+ */
+#ifndef CURDLE_B200_H
+#define CURDLE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cdl_ctx cdl_ctx;
+
+typedef enum cdl_status {
+  CDL_OK = 0,
+  CDL_ERR_NO_DEVICE = -1,   /* no CUDA device / driver: the library never falls back to the CPU */
+  CDL_ERR_CUDA = -2,        /* a CUDA runtime call failed (see cdl_last_error) */
+  CDL_ERR_INVALID_ARG = -3, /* null pointer, bad size, length mismatch (gnark MultiExp's only error) */
+  CDL_ERR_DECODE = -4,      /* malformed point / scalar encoding (gnark SetBytes / Decoder error) */
+  CDL_ERR_PROTOCOL = -5,    /* reference returns (.., err): zero challenge, bad lengths, "randomizer is zero" */
+  CDL_ERR_TOO_LARGE = -6,   /* exceeds a documented size limit of this build */
+  CDL_ERR_INTERNAL = -7
+} cdl_status;
+
+typedef struct cdl_fp { uint64_t l[6]; } cdl_fp;        /* gnark fp.Element */
+typedef struct cdl_fr { uint64_t l[4]; } cdl_fr;        /* gnark fr.Element */
+typedef struct cdl_g1_affine { cdl_fp x, y; } cdl_g1_affine;    /* gnark bls12381.G1Affine */
+typedef struct cdl_g1_jac { cdl_fp x, y, z; } cdl_g1_jac;       /* gnark bls12381.G1Jac */
+
+/* ---- context ---------------------------------------------------------- */
+int32_t cdl_create(int device, cdl_ctx** out);
+void cdl_destroy(cdl_ctx* ctx);
+const char* cdl_last_error(cdl_ctx* ctx);
+/* ABI version of this build (major << 16 | minor). */
+uint32_t cdl_abi_version(void);
+/* Device description: SM count and name (diagnostics / bench). */
+int32_t cdl_device_info(cdl_ctx* ctx, int32_t* sm_count, int32_t* clock_khz, char* name, size_t name_cap);
+
+/* ---- 1:1 gnark replacements, host pointers ----------------------------- */
+
+/* (*G1Jac).MultiExp(points, scalars, cfg): out = sum scalars[i] * points[i].
+ * Replaces all 39 call sites, e.g. curdleproof.go:72,75,109,113;
+ * msmaccumulator/msmaccumulator.go:59; innerproductargument.go:65,69,108,121,125,138;
+ * samemultiscalarargument.go:63-72,93-111; common/util.go:75,82.
+ * Infinity bases are skipped; n == 0 gives infinity.  The result is returned
+ * normalised (Z = 1, or Z = 0 for infinity) — any representative is valid
+ * because only canonical encodings are observable. */
+int32_t cdl_g1_msm(cdl_ctx* ctx, const cdl_g1_affine* points, const cdl_fr* scalars, size_t n, cdl_g1_jac* out);
+
+/* k independent MSMs in one launch; MSM j covers points/scalars
+ * [offsets[j], offsets[j+1]).  Affine results.  Covers the 4 / 6 MSMs of one
+ * IPA / SameMSM round (innerproductargument.go:108-138,
+ * samemultiscalarargument.go:93-111) and the verifier's tiny MSMs
+ * (innerproductargument.go:238,250,275,281). */
+int32_t cdl_g1_msm_batch(cdl_ctx* ctx, const cdl_g1_affine* points, const cdl_fr* scalars,
+                         const uint32_t* offsets, size_t k, cdl_g1_affine* out);
+
+/* (*G1Affine).ScalarMultiplication for n points: out[i] = s[i*scalar_stride] * in[i].
+ * scalar_stride == 0 broadcasts one scalar: the Whisk rescale Ts[i] = k*Rs[i]
+ * (common/util.go:55-63); scalar_stride == 1 gives per-element scalars:
+ * Gs'[i] = beta^-(i+1) * Gs[i] (grandproductargument.go:94-103).  The scalar is
+ * the fr.Element itself (the reference converts it with common.FrToBigInt,
+ * common/util.go:16-20). */
+int32_t cdl_g1_scalar_mul_affine(cdl_ctx* ctx, const cdl_g1_affine* in, const cdl_fr* s, size_t n,
+                                 size_t scalar_stride, cdl_g1_affine* out);
+
+/* Base folding L[i] += x * R[i], i < n, result affine in place.
+ * Replaces the serial loops innerproductargument.go:155-166 (called with x =
+ * gamma for G and gamma^-1 for G') and samemultiscalarargument.go:129-135. */
+int32_t cdl_g1_fold(cdl_ctx* ctx, cdl_g1_affine* L, const cdl_g1_affine* R, const cdl_fr* x, size_t n);
+
+/* bls12381.BatchJacobianToAffineG1 (transcript/transcript.go:26 and every Serialize). */
+int32_t cdl_g1_batch_to_affine(cdl_ctx* ctx, const cdl_g1_jac* in, size_t n, cdl_g1_affine* out);
+
+/* sum of n affine points (crs.go:41-48 Gsum / Hsum). */
+int32_t cdl_g1_sum_affine(cdl_ctx* ctx, const cdl_g1_affine* in, size_t n, cdl_g1_affine* out);
+
+/* G1Affine.Bytes() for n points -> n * 48 compressed bytes
+ * (transcript/transcript.go:35, whisk/types.go:79-84). */
+int32_t cdl_g1_compress(cdl_ctx* ctx, const cdl_g1_affine* in, size_t n, uint8_t* out48);
+
+/* G1Affine.SetBytes on n 48-byte compressed encodings, with curve and
+ * subgroup checks (whisk/types.go:86-95; Decoder in curdleproof.go:320-356).
+ * status[i] == 0 on success, else a positive reason code (1 bad flags /
+ * uncompressed, 2 non-canonical x, 3 no square root, 4 not in subgroup,
+ * 5 bad infinity padding).  Returns CDL_ERR_DECODE if any point failed. */
+int32_t cdl_g1_decompress(cdl_ctx* ctx, const uint8_t* in48, size_t n, cdl_g1_affine* out, uint8_t* status);
+
+/* ---- diagnostics / roofline ------------------------------------------- */
+/* out[i] = a[i] * b[i] in Fp (Montgomery).  K1 of SURVEY.md §7. */
+int32_t cdl_fp_mul(cdl_ctx* ctx, const cdl_fp* a, const cdl_fp* b, size_t n, cdl_fp* out);
+/* Integer-pipe peak microbenchmarks.  kind 0: independent
+ * 32-bit IMAD chains; 1: mad.wide (IMAD.WIDE) chains; 2: dependent Fp
+ * Montgomery products (practical modmul peak).  Writes the measured ops/s
+ * (IMAD/s for 0-1, modmul/s for 2) and the kernel time. */
+int32_t cdl_int_peak(cdl_ctx* ctx, int kind, int iters, double* ops_per_s, double* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CURDLE_B200_H */

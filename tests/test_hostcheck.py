@@ -1,0 +1,120 @@
+"""CPU validation of the product's field / curve source (csrc/*.cuh) against
+the oracle.  The carry-chain primitives are emulated bit-exactly on the host
+(csrc/carry.cuh), so this runs the same Montgomery / group-law code the GPU
+runs, without a GPU.  The harness is test-only."""
+import ctypes
+import os
+import random
+import subprocess
+
+import pytest
+
+from oracle import bls12381 as b
+from util import RP, RP_INV, RR_INV, aff_dec, aff_enc
+
+P, R = b.P, b.R
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def hc(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("hc") / "libhostcheck.so")
+    src = os.path.join(HERE, "hostcheck", "hostcheck.cpp")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-x", "c++", "-shared", "-fPIC", "-o", out, src], check=True)
+    return ctypes.CDLL(out)
+
+
+def pack(vals, nb):
+    return b"".join(v.to_bytes(nb, "little") for v in vals)
+
+
+def unpack(buf, nb):
+    return [int.from_bytes(buf[i:i + nb], "little") for i in range(0, len(buf), nb)]
+
+
+def run2(fn, A, B, nb=48):
+    out = ctypes.create_string_buffer(nb * len(A))
+    fn(pack(A, nb), pack(B, nb), out, len(A))
+    return unpack(out.raw, nb)
+
+
+def run1(fn, A, nb=48):
+    out = ctypes.create_string_buffer(nb * len(A))
+    fn(pack(A, nb), out, len(A))
+    return unpack(out.raw, nb)
+
+
+def tom(x):
+    return x * RP % P
+
+
+def test_fp_arithmetic(hc):
+    random.seed(1)
+    edge = [0, 1, P - 1, P - 2, RP, RP * RP % P, 2**380, P - 3, (P - 1) // 2, (P + 1) // 2]
+    vals = edge + [random.randrange(P) for _ in range(300)]
+    A = [random.choice(vals) for _ in range(1500)]
+    B = [random.choice(vals) for _ in range(1500)]
+    assert run2(hc.hc_fp_mul, [tom(a) for a in A], [tom(x) for x in B]) == [tom(a * x % P) for a, x in zip(A, B)]
+    assert run2(hc.hc_fp_mul, A, B) == [a * x * RP_INV % P for a, x in zip(A, B)]
+    assert run2(hc.hc_fp_add, A, B) == [(a + x) % P for a, x in zip(A, B)]
+    assert run2(hc.hc_fp_sub, A, B) == [(a - x) % P for a, x in zip(A, B)]
+    assert run1(hc.hc_fp_neg, A) == [(-a) % P for a in A]
+    assert run1(hc.hc_fp_from_mont, A) == [a * RP_INV % P for a in A]
+    assert run1(hc.hc_fp_to_mont, A) == [tom(a) for a in A]
+    S = A[:40]
+    assert run1(hc.hc_fp_inv, [tom(a) for a in S]) == [tom(pow(a, P - 2, P)) for a in S]
+    ok = (ctypes.c_int * len(S))()
+    out = ctypes.create_string_buffer(48 * len(S))
+    hc.hc_fp_sqrt(pack([tom(a * a % P) for a in S], 48), out, ok, len(S))
+    for a, s, o in zip(S, unpack(out.raw, 48), ok):
+        assert o == 1 and s * RP_INV % P in (a, P - a)
+    hc.hc_fp_sqrt(pack([tom(a) for a in S], 48), out, ok, len(S))
+    assert list(ok) == [int(b.fp_sqrt(a) is not None) for a in S]
+    lx = (ctypes.c_int * len(A))()
+    hc.hc_fp_lex(pack([tom(a) for a in A], 48), lx, len(A))
+    assert list(lx) == [int(a > (P - 1) // 2) for a in A]
+
+
+def test_fr_arithmetic(hc):
+    random.seed(2)
+    FA = [random.randrange(R) for _ in range(300)] + [0, 1, R - 1]
+    FB = [random.randrange(R) for _ in range(303)]
+    assert run2(hc.hc_fr_mul, FA, FB, 32) == [a * x * RR_INV % R for a, x in zip(FA, FB)]
+    assert run1(hc.hc_fr_from_mont, FA, 32) == [a * RR_INV % R for a in FA]
+
+
+def _binop(hc, op, As, Bs):
+    out = ctypes.create_string_buffer(96 * len(As))
+    hc.hc_g1_binop(op, b"".join(aff_enc(p) for p in As), b"".join(aff_enc(p) for p in Bs), out, len(As))
+    return [aff_dec(out.raw[i * 96:(i + 1) * 96]) for i in range(len(As))]
+
+
+def test_group_law_all_cases(hc):
+    random.seed(3)
+    pts = [b.g1_mul(b.G1_GEN, random.randrange(R)) for _ in range(24)]
+    As = pts[:12] + [None, pts[0], pts[1], None, pts[2]]
+    Bs = pts[12:] + [pts[3], None, b.g1_neg(pts[1]), None, pts[2]]
+    d = lambda p: b.g1_add(p, p)  # noqa: E731
+    exp = {0: lambda a, c: b.g1_add(d(a), c), 1: lambda a, c: b.g1_add(d(a), d(c)),
+           2: lambda a, c: b.g1_add(d(a), c), 3: lambda a, c: b.g1_add(d(a), d(c)),
+           4: lambda a, c: d(a), 5: lambda a, c: d(a),
+           6: b.g1_add, 7: b.g1_add, 8: b.g1_add, 9: b.g1_add}
+    for op in range(10):
+        assert _binop(hc, op, As, Bs) == [exp[op](a, c) for a, c in zip(As, Bs)], op
+    a = pts[5]
+    assert _binop(hc, 0, [a, a], [d(a), b.g1_neg(d(a))]) == [d(d(a)), None]
+    assert _binop(hc, 2, [a, a], [d(a), b.g1_neg(d(a))]) == [d(d(a)), None]
+    assert _binop(hc, 1, [a, a], [a, b.g1_neg(a)]) == [d(d(a)), None]
+    assert _binop(hc, 3, [a, a], [a, b.g1_neg(a)]) == [d(d(a)), None]
+
+
+def test_scalar_mul(hc):
+    random.seed(4)
+    pts = [b.g1_mul(b.G1_GEN, random.randrange(R)) for _ in range(6)]
+    ks = [0, 1, 2, 8, 9, 15, 16, R - 1, R - 2, R - 3, int("8" * 64, 16) % R] + [random.randrange(R) for _ in range(10)]
+    ps = [random.choice(pts) for _ in ks]
+    ps[3] = None
+    out = ctypes.create_string_buffer(96 * len(ks))
+    hc.hc_g1_scalar_mul(b"".join(aff_enc(p) for p in ps), pack(ks, 32), out, len(ks))
+    got = [aff_dec(out.raw[i * 96:(i + 1) * 96]) for i in range(len(ks))]
+    assert got == [b.g1_mul(p, k) for p, k in zip(ps, ks)]
