@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcurdle_b200.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-shared", "-Xcompiler", "-fPIC,-O2", "-Xptxas", "-v",
+    "-Xcompiler", "-fPIC,-O2", "-Xptxas", "-v",
 ]
 
 
@@ -32,24 +32,48 @@ def needs_build() -> bool:
     return any(os.path.getmtime(s) > t for s in _sources())
 
 
+def _compile_one(args):
+    src, obj = args
+    cmd = ["nvcc", "-c"] + NVCC_FLAGS + ["-o", obj, src]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    return src, res.returncode, " ".join(cmd) + "\n" + res.stdout + res.stderr
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every translation unit (in parallel) and link libcurdle_b200.so."""
     if not force and not needs_build():
         return LIB
+    from concurrent.futures import ThreadPoolExecutor
+
     units = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cu")]
     host_dir = os.path.join(CSRC, "host")
     if os.path.isdir(host_dir):
-        units += [os.path.join(host_dir, f) for f in sorted(os.listdir(host_dir)) if f.endswith(".cpp")]
-    cmd = ["nvcc"] + NVCC_FLAGS + ["-o", LIB] + units + ["-lpthread"]
-    res = subprocess.run(cmd, capture_output=True, text=True)
+        units += [os.path.join(host_dir, f) for f in sorted(os.listdir(host_dir)) if f.endswith((".cpp", ".cu"))]
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    hdr_mtime = max(os.path.getmtime(s) for s in _sources() if not s.endswith((".cu", ".cpp")))
+    jobs = []
+    objs = []
+    for u in units:
+        obj = os.path.join(objdir, os.path.basename(u) + ".o")
+        objs.append(obj)
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(u), hdr_mtime):
+            jobs.append((u, obj))
     log = os.path.join(HERE, "build.log")
-    with open(log, "w") as fh:
-        fh.write(" ".join(cmd) + "\n" + res.stdout + res.stderr)
-    if verbose or res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
+    with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 1))) as ex, open(log, "w") as fh:
+        for src, rc, out in ex.map(_compile_one, jobs):
+            fh.write(out)
+            if verbose or rc != 0:
+                sys.stderr.write(out)
+            if rc != 0:
+                raise RuntimeError(f"nvcc failed on {src} (see {log})")
+    cmd = ["nvcc", "-shared", "-o", LIB] + objs + ["-lpthread"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError(f"nvcc failed (see {log})")
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("link failed")
     return LIB
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

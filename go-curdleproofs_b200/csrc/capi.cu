@@ -3,13 +3,14 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <mutex>
 #include <string>
 #include <vector>
 
 #include "../../include/curdle_b200.h"
 #include "context.cuh"
-#include "msm_small.cuh"
+#include "launch.h"
 
 using namespace cdl;
 
@@ -43,7 +44,7 @@ int32_t cdl_create(int device, cdl_ctx** out) {
   cudaEventCreate(&c->ev0);
   cudaEventCreate(&c->ev1);
   // the small-MSM kernel stages up to ~6000 terms in shared memory
-  cudaFuncSetAttribute(k_msm_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsmMaxSmem);
+  msm_small_init();
   *out = c;
   return CDL_OK;
 }
@@ -97,7 +98,7 @@ int32_t cdl_g1_msm_batch(cdl_ctx* c, const cdl_g1_affine* points, const cdl_fr* 
     k_iota<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(d_idx, (uint32_t)total);
   }
   CDL_CUDA(c, cudaMemcpyAsync(d_tasks, tasks.data(), k * sizeof(MsmTask), cudaMemcpyHostToDevice, c->stream));
-  k_msm_small<<<(unsigned)k, kMsmThreads, msm_small_smem_bytes(max_terms), c->stream>>>(d_pts, d_idx, d_sc, d_tasks, d_out, nullptr);
+  launch_msm_small(d_pts, d_idx, d_sc, d_tasks, (int)k, max_terms, d_out, nullptr, c->stream);
   CDL_CUDA(c, cudaGetLastError());
   CDL_CUDA(c, cudaMemcpyAsync(out, d_out, k * sizeof(G1Affine), cudaMemcpyDeviceToHost, c->stream));
   CDL_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -151,8 +152,7 @@ static int32_t scalar_mul_impl(cdl_ctx* c, const cdl_g1_affine* in, const cdl_fr
   CDL_CUDA(c, cudaMemcpyAsync(d_in, in, n * sizeof(G1Affine), cudaMemcpyHostToDevice, c->stream));
   CDL_CUDA(c, cudaMemcpyAsync(d_s, s, ns * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
   if (addend) CDL_CUDA(c, cudaMemcpyAsync(d_add, addend, n * sizeof(G1Affine), cudaMemcpyHostToDevice, c->stream));
-  const int tpb = 64;
-  k_scalar_mul<<<(unsigned)((n + tpb - 1) / tpb), tpb, 0, c->stream>>>(d_in, d_s, stride ? 1 : 0, d_add, d_out, (int)n);
+  launch_scalar_mul(d_in, d_s, stride ? 1 : 0, d_add, d_out, (int)n, c->stream);
   CDL_CUDA(c, cudaGetLastError());
   CDL_CUDA(c, cudaMemcpyAsync(out, d_out, n * sizeof(G1Affine), cudaMemcpyDeviceToHost, c->stream));
   CDL_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -179,7 +179,7 @@ int32_t cdl_g1_batch_to_affine(cdl_ctx* c, const cdl_g1_jac* in, size_t n, cdl_g
   G1Affine* d_out = (G1Affine*)c->buf(4, n * sizeof(G1Affine));
   if (!d_in || !d_out) return c->fail(CDL_ERR_CUDA, "device allocation failed");
   CDL_CUDA(c, cudaMemcpyAsync(d_in, in, n * sizeof(G1Jac), cudaMemcpyHostToDevice, c->stream));
-  k_jac_to_affine<<<(unsigned)((n + 63) / 64), 64, 0, c->stream>>>(d_in, d_out, (int)n);
+  launch_jac_to_affine(d_in, d_out, (int)n, c->stream);
   CDL_CUDA(c, cudaGetLastError());
   CDL_CUDA(c, cudaMemcpyAsync(out, d_out, n * sizeof(G1Affine), cudaMemcpyDeviceToHost, c->stream));
   CDL_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -196,7 +196,7 @@ int32_t cdl_g1_compress(cdl_ctx* c, const cdl_g1_affine* in, size_t n, uint8_t* 
   uint8_t* d_out = (uint8_t*)c->buf(4, n * 48);
   if (!d_in || !d_out) return c->fail(CDL_ERR_CUDA, "device allocation failed");
   CDL_CUDA(c, cudaMemcpyAsync(d_in, in, n * sizeof(G1Affine), cudaMemcpyHostToDevice, c->stream));
-  k_compress<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(d_in, d_out, (int)n);
+  launch_compress(d_in, d_out, (int)n, c->stream);
   CDL_CUDA(c, cudaGetLastError());
   CDL_CUDA(c, cudaMemcpyAsync(out48, d_out, n * 48, cudaMemcpyDeviceToHost, c->stream));
   CDL_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -213,7 +213,7 @@ int32_t cdl_g1_decompress(cdl_ctx* c, const uint8_t* in48, size_t n, cdl_g1_affi
   uint8_t* d_st = (uint8_t*)c->buf(3, n);
   if (!d_in || !d_out || !d_st) return c->fail(CDL_ERR_CUDA, "device allocation failed");
   CDL_CUDA(c, cudaMemcpyAsync(d_in, in48, n * 48, cudaMemcpyHostToDevice, c->stream));
-  k_decompress<<<(unsigned)((n + 63) / 64), 64, 0, c->stream>>>(d_in, d_out, d_st, (int)n);
+  launch_decompress(d_in, d_out, d_st, (int)n, c->stream);
   CDL_CUDA(c, cudaGetLastError());
   CDL_CUDA(c, cudaMemcpyAsync(out, d_out, n * sizeof(G1Affine), cudaMemcpyDeviceToHost, c->stream));
   CDL_CUDA(c, cudaMemcpyAsync(status, d_st, n, cudaMemcpyDeviceToHost, c->stream));
@@ -235,7 +235,7 @@ int32_t cdl_fp_mul(cdl_ctx* c, const cdl_fp* a, const cdl_fp* b, size_t n, cdl_f
   if (!d_a || !d_b || !d_o) return c->fail(CDL_ERR_CUDA, "device allocation failed");
   CDL_CUDA(c, cudaMemcpyAsync(d_a, a, n * sizeof(Fp), cudaMemcpyHostToDevice, c->stream));
   CDL_CUDA(c, cudaMemcpyAsync(d_b, b, n * sizeof(Fp), cudaMemcpyHostToDevice, c->stream));
-  k_fp_mul<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(d_a, d_b, d_o, (int)n);
+  launch_fp_mul(d_a, d_b, d_o, (int)n, c->stream);
   CDL_CUDA(c, cudaGetLastError());
   CDL_CUDA(c, cudaMemcpyAsync(out, d_o, n * sizeof(Fp), cudaMemcpyDeviceToHost, c->stream));
   CDL_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -253,9 +253,7 @@ int32_t cdl_int_peak(cdl_ctx* c, int kind, int iters, double* ops_per_s, double*
   float best = 1e30f;
   for (int rep = 0; rep < 4; rep++) {  // rep 0 is the warm-up
     CDL_CUDA(c, cudaEventRecord(c->ev0, c->stream));
-    if (kind == 0) k_peak_imad<<<blocks, tpb, 0, c->stream>>>((uint32_t*)d, iters, 12345u + rep);
-    else if (kind == 1) k_peak_imad_wide<<<blocks, tpb, 0, c->stream>>>((uint64_t*)d, iters, 12345u + rep);
-    else k_peak_modmul<<<blocks, tpb, 0, c->stream>>>((Fp*)d, iters, 12345u + rep);
+    launch_peak(kind, d, blocks, tpb, iters, 12345u + rep, c->stream);
     CDL_CUDA(c, cudaEventRecord(c->ev1, c->stream));
     CDL_CUDA(c, cudaStreamSynchronize(c->stream));
     CDL_CUDA(c, cudaGetLastError());

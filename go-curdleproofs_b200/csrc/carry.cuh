@@ -13,10 +13,12 @@
 #if defined(__CUDACC__)
 #define CDL_HD __host__ __device__ __forceinline__
 #define CDL_D __device__ __forceinline__
-// group-law / inversion routines are real calls on the device: one copy of each
-// ~5k-instruction body per module instead of one per call site (compile time,
-// I-cache), for ~2% call overhead on a 7..16-modmul operation.
-#define CDL_FN static __host__ __device__ __noinline__
+// Group-law / inversion routines are force-inlined on the device.  (Real calls
+// were tried: ptxas passes their pointer arguments in per-warp uniform
+// registers, which a lane that early-returns and runs ahead clobbers for its
+// warp-mates — an illegal-address fault on sm_100a with CUDA 12.9.)  Kernels
+// keep the number of inlined copies low with non-unrolled loops instead.
+#define CDL_FN static __host__ __device__ __forceinline__
 #else
 #define CDL_HD inline
 #define CDL_D inline

@@ -9,9 +9,6 @@
 #include "../../include/curdle_b200.h"
 
 namespace cdl {
-constexpr size_t kMsmMaxSmem = 220 * 1024;          // dynamic shared memory opt-in for k_msm_small
-constexpr size_t kMsmMaxTerms = kMsmMaxSmem / 36;   // 36 B of staging per term
-
 __global__ void k_iota(uint32_t* out, uint32_t n) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = i;

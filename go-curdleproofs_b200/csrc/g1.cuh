@@ -321,12 +321,17 @@ CDL_FN void jac_scalar_mul(G1Jac& r, const G1Affine& p, const uint32_t* k) {
   G1Jac tab[8];  // tab[i] = (i+1) p
   jac_from_affine(tab[0], p);
   jac_dbl(tab[1], tab[0]);
+#pragma unroll 1
   for (int i = 2; i < 8; i++) jac_add_mixed(tab[i], tab[i - 1], p);
   int8_t dg[64];
   recode_w4(dg, k);
   jac_set_inf(r);
+#pragma unroll 1
   for (int i = 63; i >= 0; i--) {
-    if (i != 63) { jac_dbl(r, r); jac_dbl(r, r); jac_dbl(r, r); jac_dbl(r, r); }
+    if (i != 63) {
+#pragma unroll 1
+      for (int j = 0; j < 4; j++) jac_dbl(r, r);
+    }
     int d = dg[i];
     if (d != 0) {
       int a = d < 0 ? -d : d;

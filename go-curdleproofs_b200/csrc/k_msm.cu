@@ -19,8 +19,8 @@
 //   4. combine  : binary tree over windows, level L doubles the upper operand
 //                 4*2^L times (252 doublings on the critical path, 6 adds).
 //   5. normalise: one inversion, affine result (+ optional compressed bytes).
-#pragma once
-#include "kernels.cuh"
+#include "codec.cuh"
+#include "launch.h"
 
 namespace cdl {
 
@@ -28,11 +28,6 @@ constexpr int kMsmC = 4;
 constexpr int kMsmBuckets = 8;     // 2^(c-1)
 constexpr int kMsmWindows = 64;    // 63 signed windows (bits 0..251) + top raw window
 constexpr int kMsmThreads = kMsmBuckets * kMsmWindows;
-
-struct MsmTask {
-  uint32_t term_off;   // first term in idx[] / scalars[]
-  uint32_t term_cnt;
-};
 
 // 0x0888...8: 2^(c-1) in each of the 63 signed windows (bits 0..251)
 __device__ __forceinline__ uint32_t msm_bias_word(int i) { return i == 7 ? 0x08888888u : 0x88888888u; }
@@ -128,16 +123,15 @@ k_msm_small(const G1Affine* __restrict__ points, const uint32_t* __restrict__ id
   }
 
   // ---- phase 3: window sum S_w = sum_d d * B_d over the 8 lanes of the window
+  // steps 0..2: suffix sums R_d = sum_{j>=d} B_j (offsets 1,2,4);
+  // steps 3..5: S_w = sum_d R_d (offsets 4,2,1).  One loop => one inlined add.
   G1Xyzz other;
-#pragma unroll
-  for (int off = 1; off < kMsmBuckets; off <<= 1) {  // suffix sums R_d = sum_{j>=d} B_j
+#pragma unroll 1
+  for (int step = 0; step < 6; step++) {
+    int off = step < 3 ? (1 << step) : (4 >> (step - 3));
     xyzz_shfl_down(other, acc, off, kMsmBuckets);
-    if ((tid & 7) + off < kMsmBuckets) xyzz_add(acc, acc, other);
-  }
-#pragma unroll
-  for (int off = kMsmBuckets / 2; off >= 1; off >>= 1) {  // S_w = sum_d R_d
-    xyzz_shfl_down(other, acc, off, kMsmBuckets);
-    if ((tid & 7) < off) xyzz_add(acc, acc, other);
+    bool take = step < 3 ? ((tid & 7) + off < kMsmBuckets) : ((tid & 7) < off);
+    if (take) xyzz_add(acc, acc, other);
   }
 
   // ---- phase 4: combine windows (Jacobian: cheaper doublings)
@@ -149,12 +143,14 @@ k_msm_small(const G1Affine* __restrict__ points, const uint32_t* __restrict__ id
     win[w] = j;
   }
   __syncthreads();
+#pragma unroll 1
   for (int level = 0, active = kMsmWindows / 2; active >= 1; level++, active >>= 1) {
     G1Jac lo, hi;
     if (tid < active) {
       lo = win[2 * tid];
       hi = win[2 * tid + 1];
       int nd = kMsmC << level;
+#pragma unroll 1
       for (int i = 0; i < nd; i++) jac_dbl(hi, hi);
       jac_add(lo, lo, hi);
     }
@@ -173,10 +169,20 @@ k_msm_small(const G1Affine* __restrict__ points, const uint32_t* __restrict__ id
 }
 
 // shared memory bytes for the largest task of a launch
-inline size_t msm_small_smem_bytes(size_t max_terms) {
+static size_t msm_small_smem_bytes(size_t max_terms) {
   size_t a = max_terms * 36;                       // kp + pidx
   size_t b = (size_t)kMsmWindows * sizeof(G1Jac);  // combine scratch
   return a > b ? a : b;
+}
+
+cudaError_t msm_small_init() {
+  return cudaFuncSetAttribute(k_msm_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsmMaxSmem);
+}
+
+void launch_msm_small(const G1Affine* points, const uint32_t* idx, const Fr* scalars, const MsmTask* tasks,
+                      int ntasks, size_t max_terms, G1Affine* out_aff, uint8_t* out_c48, cudaStream_t st) {
+  k_msm_small<<<ntasks, kMsmThreads, msm_small_smem_bytes(max_terms), st>>>(points, idx, scalars, tasks, out_aff,
+                                                                             out_c48);
 }
 
 }  // namespace cdl

@@ -213,10 +213,13 @@ struct Mont {
     El tab[16];
     set_one(tab[0]);
     tab[1] = a;
+#pragma unroll 1
     for (int i = 2; i < 16; i++) mul(tab[i], tab[i - 1], a);
     set_one(r);
+#pragma unroll 1
     for (int w = NE * 8 - 1; w >= 0; w--) {
-      sqr(r, r); sqr(r, r); sqr(r, r); sqr(r, r);
+#pragma unroll 1
+      for (int j = 0; j < 4; j++) sqr(r, r);
       uint32_t d = (e[w >> 3] >> ((w & 7) * 4)) & 15;
       mul(r, r, tab[d]);  // public exponent: data-independent index (local memory on device)
     }
