@@ -10,6 +10,8 @@ from __future__ import annotations
 from .binding import (  # noqa: F401
     CdlError,
     Context,
+    CRS,
+    Rand,
     G1_AFFINE_BYTES,
     G1_JAC_BYTES,
     FR_BYTES,

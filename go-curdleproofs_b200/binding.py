@@ -65,9 +65,35 @@ def load_library():
     lib.cdl_g1_decompress.argtypes = [vp, vp, sz, vp, vp]
     lib.cdl_fp_mul.argtypes = [vp, vp, vp, sz, vp]
     lib.cdl_int_peak.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    u64, i32p = C.c_uint64, C.POINTER(C.c_int32)
+    lib.cdl_rand_new.argtypes = [u64, C.POINTER(vp)]
+    lib.cdl_rand_free.argtypes = [vp]
+    lib.cdl_rand_free.restype = None
+    lib.cdl_rand_get_frs.argtypes = [vp, sz, vp]
+    lib.cdl_rand_get_g1_affines.argtypes = [vp, vp, sz, vp]
+    lib.cdl_rand_generate_permutation.argtypes = [vp, sz, u32p]
+    lib.cdl_crs_generate.argtypes = [vp, sz, vp, C.POINTER(vp)]
+    lib.cdl_crs_from_points.argtypes = [vp, sz, vp, C.POINTER(vp)]
+    lib.cdl_crs_export.argtypes = [vp, vp, vp]
+    lib.cdl_crs_ell.argtypes = [vp]
+    lib.cdl_crs_ell.restype = sz
+    lib.cdl_crs_free.argtypes = [vp]
+    lib.cdl_crs_free.restype = None
+    lib.cdl_shuffle_permute_commit.argtypes = [vp, vp, vp, vp, u32p, vp, vp, vp, vp, vp, vp]
+    lib.cdl_prove.argtypes = [vp, vp, vp, vp, vp, vp, vp, u32p, vp, vp, vp, vp, sz, C.POINTER(sz)]
+    lib.cdl_verify.argtypes = [vp, vp, vp, sz, vp, vp, vp, vp, vp, vp, i32p]
+    lib.cdl_whisk_generate_shuffle_proof.argtypes = [vp, vp, vp, vp, vp, vp, sz]
+    lib.cdl_whisk_is_valid_shuffle_proof.argtypes = [vp, vp, vp, vp, sz, sz, vp, sz, vp, i32p]
+    lib.cdl_whisk_generate_shuffle_proof_batch.argtypes = [vp, vp, sz, vp, C.POINTER(vp), vp, vp, sz, i32p]
+    lib.cdl_whisk_is_valid_shuffle_proof_batch.argtypes = [vp, vp, sz, vp, vp, vp, sz, C.POINTER(vp), i32p, i32p]
+    lib.cdl_host_selftest.argtypes = [vp, vp, vp, vp]
+    lib.cdl_launch_count.argtypes = [vp]
+    lib.cdl_launch_count.restype = u64
+    no_status = ("cdl_destroy", "cdl_last_error", "cdl_abi_version", "cdl_rand_free", "cdl_crs_free", "cdl_crs_ell",
+                 "cdl_launch_count")
     for name in declared_symbols():
         fn = getattr(lib, name)  # AttributeError if the build lost a symbol
-        if name not in ("cdl_destroy", "cdl_last_error", "cdl_abi_version"):
+        if name not in no_status:
             fn.restype = i32
     _LIB = lib
     return lib
@@ -168,3 +194,167 @@ class Context:
         ops, ms = C.c_double(), C.c_double()
         self._chk(self.lib.cdl_int_peak(self.h, kind, iters, C.byref(ops), C.byref(ms)))
         return ops.value, ms.value
+
+
+class Rand:
+    """common.Rand (common/rand.go): deterministic SHAKE256 RNG."""
+
+    def __init__(self, seed: int):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.cdl_rand_new(seed, C.byref(h))
+        if rc != 0:
+            raise CdlError(rc, "cdl_rand_new")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.cdl_rand_free(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def get_frs(self, n: int) -> bytes:
+        out = C.create_string_buffer(max(1, n) * FR_BYTES)
+        rc = self.lib.cdl_rand_get_frs(self.h, n, out)
+        if rc != 0:
+            raise CdlError(rc, "cdl_rand_get_frs")
+        return out.raw[: n * FR_BYTES]
+
+    def get_fr(self) -> bytes:
+        return self.get_frs(1)
+
+    def generate_permutation(self, n: int):
+        out = (C.c_uint32 * max(1, n))()
+        rc = self.lib.cdl_rand_generate_permutation(self.h, n, out)
+        if rc != 0:
+            raise CdlError(rc, "cdl_rand_generate_permutation")
+        return list(out[:n])
+
+
+class CRS:
+    """curdleproof.CRS (crs.go:10-18), device resident."""
+
+    def __init__(self, ctx: "Context", handle):
+        self.ctx = ctx
+        self.h = handle
+
+    @property
+    def ell(self) -> int:
+        return self.ctx.lib.cdl_crs_ell(self.h)
+
+    def export(self) -> bytes:
+        """Gs[ell] | Hs[4] | H | Gt | Gu | Gsum | Hsum as affine points."""
+        out = C.create_string_buffer((self.ell + 9) * G1_AFFINE_BYTES)
+        self.ctx._chk(self.ctx.lib.cdl_crs_export(self.ctx.h, self.h, out))
+        return out.raw
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.ctx.lib.cdl_crs_free(self.h)
+        self.h = None
+
+    __del__ = close
+
+
+def _ctx_rand_get_g1_affines(self, rand: Rand, n: int) -> bytes:
+    out = C.create_string_buffer(max(1, n) * G1_AFFINE_BYTES)
+    self._chk(self.lib.cdl_rand_get_g1_affines(self.h, rand.h, n, out))
+    return out.raw[: n * G1_AFFINE_BYTES]
+
+
+def _ctx_generate_crs(self, ell: int, rand: Rand) -> CRS:
+    """curdleproof.GenerateCRS (crs.go:20-59)."""
+    h = C.c_void_p()
+    self._chk(self.lib.cdl_crs_generate(self.h, ell, rand.h, C.byref(h)))
+    return CRS(self, h)
+
+
+def _ctx_crs_from_points(self, ell: int, points: bytes) -> CRS:
+    h = C.c_void_p()
+    self._chk(self.lib.cdl_crs_from_points(self.h, ell, points, C.byref(h)))
+    return CRS(self, h)
+
+
+def _ctx_shuffle_permute_commit(self, crs: CRS, Rs: bytes, Ss: bytes, perm, k: bytes, rand: Rand):
+    """common.ShufflePermuteCommit -> (Ts, Us, M jac, rs_m)."""
+    ell = crs.ell
+    Ts = C.create_string_buffer(ell * G1_AFFINE_BYTES)
+    Us = C.create_string_buffer(ell * G1_AFFINE_BYTES)
+    M = C.create_string_buffer(G1_JAC_BYTES)
+    rs_m = C.create_string_buffer(4 * FR_BYTES)
+    p = (C.c_uint32 * ell)(*perm)
+    self._chk(self.lib.cdl_shuffle_permute_commit(self.h, crs.h, Rs, Ss, p, k, rand.h, Ts, Us, M, rs_m))
+    return Ts.raw, Us.raw, M.raw, rs_m.raw
+
+
+def _ctx_prove(self, crs: CRS, Rs, Ss, Ts, Us, M, perm, k, rs_m, rand: Rand) -> bytes:
+    """curdleproof.Prove + Proof.Serialize."""
+    ell = crs.ell
+    cap = 48 * (18 + 10 * 32) + 32 * 7 + 40
+    out = C.create_string_buffer(cap)
+    n = C.c_size_t()
+    p = (C.c_uint32 * ell)(*perm)
+    self._chk(self.lib.cdl_prove(self.h, crs.h, Rs, Ss, Ts, Us, M, p, k, rs_m, rand.h, out, cap, C.byref(n)))
+    return out.raw[: n.value]
+
+
+def _ctx_verify(self, crs: CRS, proof: bytes, Rs, Ss, Ts, Us, M, rand: Rand) -> bool:
+    """Proof.FromReader + curdleproof.Verify; raises CdlError where the reference returns an error."""
+    ok = C.c_int32()
+    self._chk(self.lib.cdl_verify(self.h, crs.h, proof, len(proof), Rs, Ss, Ts, Us, M, rand.h, C.byref(ok)))
+    return bool(ok.value)
+
+
+def _ctx_whisk_generate(self, crs: CRS, pre: bytes, rand: Rand, proof_size: int = 4576):
+    """whisk.GenerateWhiskShuffleProof -> (post_trackers, proof)."""
+    ell = crs.ell
+    post = C.create_string_buffer(ell * 96)
+    proof = C.create_string_buffer(proof_size)
+    self._chk(self.lib.cdl_whisk_generate_shuffle_proof(self.h, crs.h, pre, rand.h, post, proof, proof_size))
+    return post.raw, proof.raw
+
+
+def _ctx_whisk_is_valid(self, crs: CRS, pre: bytes, post: bytes, proof: bytes, rand: Rand) -> bool:
+    """whisk.IsValidWhiskShuffleProof."""
+    ok = C.c_int32()
+    self._chk(self.lib.cdl_whisk_is_valid_shuffle_proof(self.h, crs.h, pre, post, len(pre) // 96, len(post) // 96,
+                                                        proof, len(proof), rand.h, C.byref(ok)))
+    return bool(ok.value)
+
+
+def _ctx_whisk_generate_batch(self, crs: CRS, pre: bytes, rands, proof_size: int = 4576):
+    B = len(rands)
+    ell = crs.ell
+    post = C.create_string_buffer(B * ell * 96)
+    proofs = C.create_string_buffer(B * proof_size)
+    status = (C.c_int32 * B)()
+    rh = (C.c_void_p * B)(*[r.h for r in rands])
+    self._chk(self.lib.cdl_whisk_generate_shuffle_proof_batch(self.h, crs.h, B, pre, rh, post, proofs, proof_size, status))
+    return post.raw, proofs.raw, list(status)
+
+
+def _ctx_whisk_is_valid_batch(self, crs: CRS, pre: bytes, post: bytes, proofs: bytes, rands, proof_size: int = 4576):
+    B = len(rands)
+    ok = (C.c_int32 * B)()
+    status = (C.c_int32 * B)()
+    rh = (C.c_void_p * B)(*[r.h for r in rands])
+    self._chk(self.lib.cdl_whisk_is_valid_shuffle_proof_batch(self.h, crs.h, B, pre, post, proofs, proof_size, rh, ok, status))
+    return list(ok), list(status)
+
+
+def _ctx_launch_count(self) -> int:
+    return int(self.lib.cdl_launch_count(self.h))
+
+
+Context.rand_get_g1_affines = _ctx_rand_get_g1_affines
+Context.generate_crs = _ctx_generate_crs
+Context.crs_from_points = _ctx_crs_from_points
+Context.shuffle_permute_commit = _ctx_shuffle_permute_commit
+Context.prove = _ctx_prove
+Context.verify = _ctx_verify
+Context.whisk_generate_shuffle_proof = _ctx_whisk_generate
+Context.whisk_is_valid_shuffle_proof = _ctx_whisk_is_valid
+Context.whisk_generate_shuffle_proof_batch = _ctx_whisk_generate_batch
+Context.whisk_is_valid_shuffle_proof_batch = _ctx_whisk_is_valid_batch
+Context.launch_count = _ctx_launch_count

@@ -14,6 +14,13 @@
 
 using namespace cdl;
 
+namespace cdl {
+static __global__ void k_iota(uint32_t* out, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = i;
+}
+}  // namespace cdl
+
 static_assert(sizeof(Fp) == sizeof(cdl_fp), "fp layout");
 static_assert(sizeof(Fr) == sizeof(cdl_fr), "fr layout");
 static_assert(sizeof(G1Affine) == sizeof(cdl_g1_affine), "affine layout");
@@ -49,9 +56,12 @@ int32_t cdl_create(int device, cdl_ctx** out) {
   return CDL_OK;
 }
 
+void cdl_engine_free_(void* engine);  // capi_protocol.cu
+
 void cdl_destroy(cdl_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  if (c->engine) cdl_engine_free_(c->engine);
   c->free_all();
   cudaEventDestroy(c->ev0);
   cudaEventDestroy(c->ev1);
@@ -83,6 +93,8 @@ int32_t cdl_g1_msm_batch(cdl_ctx* c, const cdl_g1_affine* points, const cdl_fr* 
     if (offsets[j + 1] < offsets[j]) return c->fail(CDL_ERR_INVALID_ARG, "msm_batch: offsets not monotone");
     tasks[j].term_off = offsets[j];
     tasks[j].term_cnt = offsets[j + 1] - offsets[j];
+    tasks[j].out_idx = (uint32_t)j;
+    tasks[j].pad = 0;
     if (tasks[j].term_cnt > max_terms) max_terms = tasks[j].term_cnt;
   }
   if (max_terms > kMsmMaxTerms) return c->fail(CDL_ERR_TOO_LARGE, "msm: %zu terms exceed the small-MSM limit %zu", max_terms, (size_t)kMsmMaxTerms);

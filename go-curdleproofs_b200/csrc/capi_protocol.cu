@@ -1,0 +1,496 @@
+// Protocol-level C ABI: common.Rand, CRS, ShufflePermuteCommit, Prove, Verify and
+// the Whisk wrappers (single and batched), on top of the batched engine.
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <vector>
+
+#include "host/engine.hpp"
+
+using cdlh::Engine;
+using cdlh::Fr;
+using cdlh::Layout;
+
+static_assert(sizeof(Fr) == sizeof(cdl_fr), "host fr layout");
+
+namespace {
+
+// BLS12-381 G1 generator, affine Montgomery form (gnark bls12381.Generators())
+const uint32_t kGenX[12] = {0xfd530c16u, 0x5cb38790u, 0x9976fff5u, 0x7817fc67u, 0x143ba1c1u, 0x154f95c7u,
+                            0xf3d0e747u, 0xf0ae6acdu, 0x21dbf440u, 0xedce6eccu, 0x9e0bfb75u, 0x12017741u};
+const uint32_t kGenY[12] = {0x0ce72271u, 0xbaac93d5u, 0x7918fd8eu, 0x8c22631au, 0x570725ceu, 0xdd595f13u,
+                            0x50405194u, 0x51ac5829u, 0xad0059c0u, 0x0e1c8c3fu, 0x5008a26au, 0x0bbc3efcu};
+const uint64_t kFpOne[6] = {0x760900000002fffdull, 0xebf4000bc40c0002ull, 0x5f48985753c758baull,
+                            0x77ce585370525745ull, 0x5c071a97a256ec6dull, 0x15f65ec3fa80e493ull};
+
+Engine* engine_of(cdl_ctx* c) {
+  if (!c->engine) c->engine = new Engine(c);
+  return static_cast<Engine*>(c->engine);
+}
+
+void affine_to_jac(cdl_g1_jac* out, const cdl_g1_affine& a) {
+  bool inf = true;
+  for (int i = 0; i < 6; i++) inf = inf && a.x.l[i] == 0 && a.y.l[i] == 0;
+  if (inf) {
+    memcpy(out->x.l, kFpOne, 48);
+    memcpy(out->y.l, kFpOne, 48);
+    memset(out->z.l, 0, 48);
+  } else {
+    out->x = a.x;
+    out->y = a.y;
+    memcpy(out->z.l, kFpOne, 48);
+  }
+}
+
+// n draws a_i from r, points a_i * G (rand.go:72-95), written to pool[dst..]
+int32_t rand_points_to_pool(Engine* E, cdl_rand* r, uint32_t gen_slot, uint32_t dst, size_t n) {
+  if (!n) return CDL_OK;
+  std::vector<Fr> sc(n);
+  r->r.get_frs(sc.data(), n);
+  std::vector<cdl::ElemOp> ops(n);
+  for (size_t i = 0; i < n; i++) ops[i] = cdl::ElemOp{gen_slot, cdl::kNoPoint, (uint32_t)(dst + i), (uint32_t)i};
+  return E->run_elem(ops, sc);
+}
+
+int32_t put_generator(Engine* E, uint32_t slot) {
+  cdl_g1_affine g;
+  memcpy(g.x.l, kGenX, 48);
+  memcpy(g.y.l, kGenY, 48);
+  return E->upload_points(slot, &g, 1);
+}
+
+// finish a CRS object from pool[0 .. ell+9): copies the image to its own device buffer, caches encodings
+int32_t crs_finish(cdl_ctx* c, Engine* E, const Layout& L, cdl_crs** out) {
+  std::unique_ptr<cdl_crs> crs(new cdl_crs());
+  crs->ctx = c;
+  crs->ell = L.ell;
+  int32_t rc = E->set_infinity(L.INF, 1);
+  if (rc) return rc;
+  if (cudaMalloc(&crs->d_points, (size_t)L.crs_size * sizeof(cdl::G1Affine)) != cudaSuccess)
+    return c->fail(CDL_ERR_CUDA, "crs allocation failed");
+  std::vector<uint32_t> src(L.crs_size);
+  for (uint32_t i = 0; i < L.crs_size; i++) src[i] = i;
+  if ((rc = E->compress(src, crs->enc))) { cudaFree(crs->d_points); return rc; }
+  std::vector<cdl_g1_affine> tmp(L.crs_size);
+  if ((rc = E->download_points(0, tmp.data(), L.crs_size))) { cudaFree(crs->d_points); return rc; }
+  if (cudaMemcpy(crs->d_points, tmp.data(), (size_t)L.crs_size * sizeof(cdl::G1Affine), cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaFree(crs->d_points);
+    return c->fail(CDL_ERR_CUDA, "crs upload failed");
+  }
+  *out = crs.release();
+  return CDL_OK;
+}
+
+struct Prep {
+  Engine* E;
+  Layout L;
+};
+
+// common prologue of the protocol calls
+int32_t begin_call(cdl_ctx* c, const cdl_crs* crs, size_t B, Engine** E, Layout* L) {
+  if (crs->ctx != c) return c->fail(CDL_ERR_INVALID_ARG, "crs belongs to another context");
+  CDL_CUDA(c, cudaSetDevice(c->device));
+  *E = engine_of(c);
+  *L = Layout(crs->ell);
+  int32_t rc = (*E)->ensure_pool((size_t)L->crs_size + B * (size_t)L->inst_size);
+  if (rc) return rc;
+  return (*E)->load_crs(*L, crs);
+}
+
+}  // namespace
+
+extern "C" {
+
+void cdl_engine_free_(void* engine) { delete static_cast<Engine*>(engine); }
+
+uint64_t cdl_launch_count(cdl_ctx* c) { return c && c->engine ? static_cast<Engine*>(c->engine)->launches : 0; }
+
+int32_t cdl_host_selftest(uint8_t* out32, const cdl_fr* a, const cdl_fr* b, cdl_fr* fr_out) {
+  if (!out32 || !a || !b || !fr_out) return CDL_ERR_INVALID_ARG;
+  cdlh::Transcript t("test protocol");
+  t.append_message("some label", reinterpret_cast<const uint8_t*>("some data"), 9);
+  t.challenge_bytes("challenge", out32, 32);
+  Fr x, y;
+  memcpy(&x, a, 32);
+  memcpy(&y, b, 32);
+  Fr t1 = cdlh::fr_sub(cdlh::fr_add(cdlh::fr_mul(x, y), x), y);
+  Fr r = cdlh::fr_mul(cdlh::fr_inv(t1), cdlh::fr_pow_u64(x, 5));
+  memcpy(fr_out, &r, 32);
+  return CDL_OK;
+}
+
+// ------------------------------------------------------------------ Rand
+int32_t cdl_rand_new(uint64_t seed, cdl_rand** out) {
+  if (!out) return CDL_ERR_INVALID_ARG;
+  *out = new cdl_rand(seed);
+  return CDL_OK;
+}
+void cdl_rand_free(cdl_rand* r) { delete r; }
+int32_t cdl_rand_get_frs(cdl_rand* r, size_t n, cdl_fr* out) {
+  if (!r || (n && !out)) return CDL_ERR_INVALID_ARG;
+  r->r.get_frs(reinterpret_cast<Fr*>(out), n);
+  return CDL_OK;
+}
+int32_t cdl_rand_generate_permutation(cdl_rand* r, size_t n, uint32_t* out) {
+  if (!r || (n && !out)) return CDL_ERR_INVALID_ARG;
+  std::vector<uint32_t> p = r->r.generate_permutation(n);
+  memcpy(out, p.data(), n * 4);
+  return CDL_OK;
+}
+int32_t cdl_rand_get_g1_affines(cdl_ctx* c, cdl_rand* r, size_t n, cdl_g1_affine* out) {
+  if (!c || !r || (n && !out)) return CDL_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(c->mu);
+  CDL_CUDA(c, cudaSetDevice(c->device));
+  Engine* E = engine_of(c);
+  int32_t rc;
+  if ((rc = E->ensure_pool(n + 1)) || (rc = put_generator(E, 0)) || (rc = rand_points_to_pool(E, r, 0, 1, n))) return rc;
+  return E->download_points(1, out, n);
+}
+
+// ------------------------------------------------------------------ CRS
+int32_t cdl_crs_generate(cdl_ctx* c, size_t ell, cdl_rand* r, cdl_crs** out) {
+  if (!c || !r || !out || ell == 0 || ell > (1u << 24)) return CDL_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(c->mu);
+  CDL_CUDA(c, cudaSetDevice(c->device));
+  Engine* E = engine_of(c);
+  Layout L((uint32_t)ell);
+  int32_t rc;
+  if ((rc = E->ensure_pool(L.crs_size + 1))) return rc;
+  const uint32_t gen = L.crs_size;  // scratch slot after the CRS image
+  if ((rc = put_generator(E, gen))) return rc;
+  // draw order: Gs (ell), Hs (4), H, Gt, Gu   (crs.go:21-40); these are contiguous in the image
+  if ((rc = rand_points_to_pool(E, r, gen, L.Gs, ell + 7))) return rc;
+  // Gsum = sum Gs, Hsum = sum Hs   (crs.go:41-48)
+  cdlh::MsmStage st;
+  st.idx.resize(ell + 4);
+  st.sc.assign(ell + 4, cdlh::FR_ONE);
+  for (uint32_t i = 0; i < ell + 4; i++) st.idx[i] = i;
+  st.tasks.push_back(cdl::MsmTask{0, (uint32_t)ell, L.Gsum, 0});
+  st.tasks.push_back(cdl::MsmTask{(uint32_t)ell, 4, L.Hsum, 0});
+  if ((rc = E->run_msm(st))) return rc;
+  return crs_finish(c, E, L, out);
+}
+
+int32_t cdl_crs_from_points(cdl_ctx* c, size_t ell, const cdl_g1_affine* points, cdl_crs** out) {
+  if (!c || !points || !out || ell == 0 || ell > (1u << 24)) return CDL_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(c->mu);
+  CDL_CUDA(c, cudaSetDevice(c->device));
+  Engine* E = engine_of(c);
+  Layout L((uint32_t)ell);
+  int32_t rc;
+  if ((rc = E->ensure_pool(L.crs_size + 1)) || (rc = E->upload_points(0, points, ell + 9))) return rc;
+  return crs_finish(c, E, L, out);
+}
+
+int32_t cdl_crs_export(cdl_ctx* c, const cdl_crs* crs, cdl_g1_affine* points) {
+  if (!c || !crs || !points) return CDL_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(c->mu);
+  CDL_CUDA(c, cudaSetDevice(c->device));
+  CDL_CUDA(c, cudaMemcpy(points, crs->d_points, (size_t)(crs->ell + 9) * sizeof(cdl::G1Affine), cudaMemcpyDeviceToHost));
+  return CDL_OK;
+}
+
+size_t cdl_crs_ell(const cdl_crs* crs) { return crs ? crs->ell : 0; }
+
+void cdl_crs_free(cdl_crs* crs) {
+  if (!crs) return;
+  if (crs->d_points) { cudaSetDevice(crs->ctx->device); cudaFree(crs->d_points); }
+  delete crs;
+}
+
+// ------------------------------------------------------------------ ShufflePermuteCommit
+int32_t cdl_shuffle_permute_commit(cdl_ctx* c, const cdl_crs* crs, const cdl_g1_affine* Rs, const cdl_g1_affine* Ss,
+                                   const uint32_t* perm, const cdl_fr* k, cdl_rand* r, cdl_g1_affine* Ts,
+                                   cdl_g1_affine* Us, cdl_g1_jac* M, cdl_fr* rs_m) {
+  if (!c || !crs || !Rs || !Ss || !perm || !k || !r || !Ts || !Us || !M || !rs_m) return CDL_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(c->mu);
+  Engine* E;
+  Layout L(1);
+  int32_t rc = begin_call(c, crs, 1, &E, &L);
+  if (rc) return rc;
+  const uint32_t ell = L.ell, base = L.base(0);
+  for (uint32_t i = 0; i < ell; i++)
+    if (perm[i] >= ell) return c->fail(CDL_ERR_INVALID_ARG, "permutation entry out of range");
+  if ((rc = E->upload_points(base + L.Rs, Rs, ell)) || (rc = E->upload_points(base + L.Ss, Ss, ell))) return rc;
+  std::vector<std::vector<uint32_t>> perms(1, std::vector<uint32_t>(perm, perm + ell));
+  std::vector<Fr> ks(1);
+  memcpy(&ks[0], k, 32);
+  std::vector<cdl_rand*> rands(1, r);
+  std::vector<std::vector<Fr>> rsm;
+  if ((rc = E->shuffle_permute_commit(L, 1, perms, ks, rands, rsm))) return rc;
+  cdl_g1_affine m_aff;
+  if ((rc = E->download_points(base + L.Ts, Ts, ell)) || (rc = E->download_points(base + L.Us, Us, ell)) ||
+      (rc = E->download_points(base + L.M, &m_aff, 1)))
+    return rc;
+  affine_to_jac(M, m_aff);
+  memcpy(rs_m, rsm[0].data(), 4 * 32);
+  return CDL_OK;
+}
+
+// ------------------------------------------------------------------ Prove
+int32_t cdl_prove(cdl_ctx* c, const cdl_crs* crs, const cdl_g1_affine* Rs, const cdl_g1_affine* Ss,
+                  const cdl_g1_affine* Ts, const cdl_g1_affine* Us, const cdl_g1_jac* M, const uint32_t* perm,
+                  const cdl_fr* k, const cdl_fr* rs_m, cdl_rand* r, uint8_t* proof, size_t proof_cap,
+                  size_t* proof_len) {
+  if (!c || !crs || !Rs || !Ss || !Ts || !Us || !M || !perm || !k || !rs_m || !r || !proof || !proof_len)
+    return CDL_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(c->mu);
+  Engine* E;
+  Layout L(1);
+  int32_t rc = begin_call(c, crs, 1, &E, &L);
+  if (rc) return rc;
+  const uint32_t ell = L.ell, base = L.base(0);
+  for (uint32_t i = 0; i < ell; i++)
+    if (perm[i] >= ell) return c->fail(CDL_ERR_INVALID_ARG, "permutation entry out of range");
+  if ((rc = E->upload_points(base + L.Rs, Rs, ell)) || (rc = E->upload_points(base + L.Ss, Ss, ell)) ||
+      (rc = E->upload_points(base + L.Ts, Ts, ell)) || (rc = E->upload_points(base + L.Us, Us, ell)) ||
+      (rc = E->upload_jac(base + L.M, M, 1)))
+    return rc;
+  std::vector<std::vector<uint32_t>> perms(1, std::vector<uint32_t>(perm, perm + ell));
+  std::vector<Fr> ks(1);
+  memcpy(&ks[0], k, 32);
+  std::vector<std::vector<Fr>> rsm(1, std::vector<Fr>(4));
+  memcpy(rsm[0].data(), rs_m, 4 * 32);
+  std::vector<cdl_rand*> rands(1, r);
+  std::vector<std::vector<uint8_t>> proofs;
+  std::vector<int32_t> status;
+  std::vector<std::string> errs;
+  std::vector<uint8_t> inst_enc;
+  if ((rc = E->prove(L, 1, crs, perms, ks, rsm, rands, proofs, status, errs, inst_enc))) return rc;
+  if (status[0] != CDL_OK) return c->fail(status[0], "%s", errs[0].c_str());
+  *proof_len = proofs[0].size();
+  if (proofs[0].size() > proof_cap) return c->fail(CDL_ERR_INVALID_ARG, "proof buffer too small: need %zu bytes", proofs[0].size());
+  memcpy(proof, proofs[0].data(), proofs[0].size());
+  return CDL_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------ Verify helpers
+namespace {
+
+// Decode B serialized proofs (+ optional leading M) and their instance encodings into
+// the pool: fills pp[b] (indices, encodings, scalars) and marks decode failures.
+// inst_enc[b] must hold Rs | Ss | Ts | Us encodings (4*ell*48 B) when decode_instance.
+int32_t load_proofs(Engine* E, const Layout& L, uint32_t B, const uint8_t* const* proof_ptr, const size_t* proof_len,
+                    bool with_m, const uint8_t* const* m_enc, const std::vector<const uint8_t*>& inst_enc,
+                    bool decode_instance, std::vector<Engine::ParsedProof>& pp) {
+  const uint32_t ell = L.ell;
+  pp.assign(B, Engine::ParsedProof());
+  std::vector<uint8_t> enc;
+  std::vector<uint32_t> dst;
+  std::vector<uint32_t> owner;  // instance of each queued point
+  for (uint32_t b = 0; b < B; b++) {
+    Engine::ParsedProof& q = pp[b];
+    q.inst_enc = inst_enc[b];
+    cdlh::WireProof w;
+    size_t used = 0;
+    std::string e = cdlh::parse_wire_proof(proof_ptr[b], proof_len[b], with_m, w, &used);
+    if (!e.empty()) { q.err = "decoding proof: " + e; continue; }
+    q.sc.resize(7);
+    bool sc_ok = true;
+    for (int i = 0; i < 7; i++) sc_ok = sc_ok && cdlh::fr_from_bytes_be_canonical(q.sc[i], w.scalars[i]);
+    if (!sc_ok) { q.err = "decoding proof: scalar is not canonical"; continue; }
+    memcpy(q.lens, w.lens, sizeof q.lens);
+    if (w.points.size() + (with_m ? 0 : 1) > 19 + 10 * 32) { q.err = "decoding proof: too many points"; continue; }
+    const uint32_t base = L.base(b);
+    uint32_t slot = base + L.PP;
+    if (!with_m) {  // M comes from the caller (already in the pool at L.M)
+      q.pt.push_back(base + L.M);
+      q.enc.push_back(m_enc[b]);
+    }
+    for (const uint8_t* p : w.points) {
+      q.pt.push_back(slot);
+      q.enc.push_back(p);
+      enc.insert(enc.end(), p, p + 48);
+      dst.push_back(slot++);
+      owner.push_back(b);
+    }
+    if (decode_instance) {
+      enc.insert(enc.end(), inst_enc[b], inst_enc[b] + (size_t)4 * ell * 48);
+      for (uint32_t i = 0; i < 4 * ell; i++) { dst.push_back(base + L.Rs + i); owner.push_back(b); }
+    }
+    q.ok = true;
+  }
+  std::vector<uint8_t> st;
+  int32_t rc = E->decompress(enc.data(), dst, st);
+  if (rc) return rc;
+  for (size_t i = 0; i < st.size(); i++)
+    if (st[i] && pp[owner[i]].ok) {
+      pp[owner[i]].ok = false;
+      pp[owner[i]].err = "decoding point: rejected encoding (reason " + std::to_string((int)st[i]) + ")";
+    }
+  return CDL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t cdl_verify(cdl_ctx* c, const cdl_crs* crs, const uint8_t* proof, size_t proof_len,
+                   const cdl_g1_affine* Rs, const cdl_g1_affine* Ss, const cdl_g1_affine* Ts,
+                   const cdl_g1_affine* Us, const cdl_g1_jac* M, cdl_rand* r, int32_t* ok) {
+  if (!c || !crs || !proof || !Rs || !Ss || !Ts || !Us || !M || !r || !ok) return CDL_ERR_INVALID_ARG;
+  *ok = 0;
+  std::lock_guard<std::mutex> lk(c->mu);
+  Engine* E;
+  Layout L(1);
+  int32_t rc = begin_call(c, crs, 1, &E, &L);
+  if (rc) return rc;
+  const uint32_t ell = L.ell, base = L.base(0);
+  if ((rc = E->upload_points(base + L.Rs, Rs, ell)) || (rc = E->upload_points(base + L.Ss, Ss, ell)) ||
+      (rc = E->upload_points(base + L.Ts, Ts, ell)) || (rc = E->upload_points(base + L.Us, Us, ell)) ||
+      (rc = E->upload_jac(base + L.M, M, 1)))
+    return rc;
+  std::vector<uint32_t> src(4 * ell + 1);
+  for (uint32_t i = 0; i < 4 * ell; i++) src[i] = base + L.Rs + i;
+  src[4 * ell] = base + L.M;
+  std::vector<uint8_t> inst;
+  if ((rc = E->compress(src, inst))) return rc;
+  const uint8_t* m_enc = inst.data() + (size_t)4 * ell * 48;
+  std::vector<const uint8_t*> inst_ptr(1, inst.data());
+  std::vector<Engine::ParsedProof> pp;
+  if ((rc = load_proofs(E, L, 1, &proof, &proof_len, false, &m_enc, inst_ptr, false, pp))) return rc;
+  if (!pp[0].ok) return c->fail(CDL_ERR_DECODE, "%s", pp[0].err.c_str());
+  std::vector<cdl_rand*> rands(1, r);
+  std::vector<int32_t> verdict, status;
+  std::vector<std::string> errs;
+  if ((rc = E->verify(L, 1, crs, pp, rands, verdict, status, errs))) return rc;
+  if (status[0] != CDL_OK) return c->fail(status[0], "%s", errs[0].c_str());
+  *ok = verdict[0];
+  return CDL_OK;
+}
+
+// ------------------------------------------------------------------ Whisk
+int32_t cdl_whisk_generate_shuffle_proof_batch(cdl_ctx* c, const cdl_crs* crs, size_t B, const uint8_t* pre_trackers,
+                                               cdl_rand* const* rands_in, uint8_t* post_trackers, uint8_t* proofs_out,
+                                               size_t proof_cap, int32_t* status_out) {
+  if (!c || !crs || !pre_trackers || !rands_in || !post_trackers || !proofs_out || !status_out || B == 0)
+    return CDL_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(c->mu);
+  Engine* E;
+  Layout L(1);
+  int32_t rc = begin_call(c, crs, B, &E, &L);
+  if (rc) return rc;
+  const uint32_t ell = L.ell;
+  std::vector<cdl_rand*> rands(rands_in, rands_in + B);
+  // whisk.go:64-71: permutation, then k
+  std::vector<std::vector<uint32_t>> perms(B);
+  std::vector<Fr> ks(B);
+  for (size_t b = 0; b < B; b++) {
+    perms[b] = rands[b]->r.generate_permutation(ell);
+    ks[b] = rands[b]->r.get_fr();
+  }
+  // whisk.go:73-80: trackers -> points (SetBytes with subgroup check), rG -> Rs, krG -> Ss
+  std::vector<uint32_t> dst((size_t)B * 2 * ell);
+  for (size_t b = 0; b < B; b++)
+    for (uint32_t i = 0; i < ell; i++) {
+      dst[(b * ell + i) * 2] = L.base((uint32_t)b) + L.Rs + i;
+      dst[(b * ell + i) * 2 + 1] = L.base((uint32_t)b) + L.Ss + i;
+    }
+  std::vector<uint8_t> st;
+  if ((rc = E->decompress(pre_trackers, dst, st))) return rc;
+  bool any_bad = false;
+  for (size_t b = 0; b < B; b++) {
+    status_out[b] = CDL_OK;
+    for (uint32_t i = 0; i < 2 * ell; i++)
+      if (st[b * 2 * ell + i]) { status_out[b] = CDL_ERR_DECODE; any_bad = true; }
+  }
+  std::vector<std::vector<Fr>> rsm;
+  if ((rc = E->shuffle_permute_commit(L, (uint32_t)B, perms, ks, rands, rsm))) return rc;
+  std::vector<std::vector<uint8_t>> proofs;
+  std::vector<int32_t> status;
+  std::vector<std::string> errs;
+  std::vector<uint8_t> inst_enc;
+  if ((rc = E->prove(L, (uint32_t)B, crs, perms, ks, rsm, rands, proofs, status, errs, inst_enc))) return rc;
+  const size_t per_inst = (size_t)(4 * ell + 1) * 48;
+  for (size_t b = 0; b < B; b++) {
+    uint8_t* po = proofs_out + b * proof_cap;
+    memset(po, 0, proof_cap);
+    uint8_t* post = post_trackers + b * (size_t)ell * 96;
+    if (status_out[b] != CDL_OK) { memset(post, 0, (size_t)ell * 96); continue; }
+    if (status[b] != CDL_OK) { status_out[b] = status[b]; c->fail(status[b], "generating proof: %s", errs[b].c_str()); any_bad = true; continue; }
+    const uint8_t* ie = inst_enc.data() + b * per_inst;
+    if (48 + proofs[b].size() > proof_cap) { status_out[b] = CDL_ERR_INVALID_ARG; any_bad = true; continue; }
+    memcpy(po, ie + (size_t)4 * ell * 48, 48);  // M   (whisk/types.go:57-61)
+    memcpy(po + 48, proofs[b].data(), proofs[b].size());
+    for (uint32_t i = 0; i < ell; i++) {  // NewWhiskTracker(Ts[i], Us[i])  (whisk.go:108-111)
+      memcpy(post + 96 * i, ie + ((size_t)2 * ell + i) * 48, 48);
+      memcpy(post + 96 * i + 48, ie + ((size_t)3 * ell + i) * 48, 48);
+    }
+  }
+  (void)any_bad;
+  return CDL_OK;
+}
+
+int32_t cdl_whisk_generate_shuffle_proof(cdl_ctx* c, const cdl_crs* crs, const uint8_t* pre_trackers, cdl_rand* r,
+                                         uint8_t* post_trackers, uint8_t* proof, size_t proof_cap) {
+  int32_t status = CDL_OK;
+  cdl_rand* rr[1] = {r};
+  int32_t rc = cdl_whisk_generate_shuffle_proof_batch(c, crs, 1, pre_trackers, rr, post_trackers, proof, proof_cap, &status);
+  if (rc) return rc;
+  if (status == CDL_ERR_DECODE) return c->fail(status, "getting points: a pre-shuffle tracker failed to decode");
+  if (status == CDL_ERR_INVALID_ARG) return c->fail(status, "proof buffer too small");
+  return status;
+}
+
+int32_t cdl_whisk_is_valid_shuffle_proof_batch(cdl_ctx* c, const cdl_crs* crs, size_t B, const uint8_t* pre_trackers,
+                                               const uint8_t* post_trackers, const uint8_t* proofs, size_t proof_len,
+                                               cdl_rand* const* rands_in, int32_t* ok, int32_t* status_out) {
+  if (!c || !crs || !pre_trackers || !post_trackers || !proofs || !rands_in || !ok || !status_out || B == 0)
+    return CDL_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(c->mu);
+  Engine* E;
+  Layout L(1);
+  int32_t rc = begin_call(c, crs, B, &E, &L);
+  if (rc) return rc;
+  const uint32_t ell = L.ell;
+  // instance encodings in transcript order Rs | Ss | Ts | Us   (whisk.go:31-44)
+  std::vector<uint8_t> inst((size_t)B * 4 * ell * 48);
+  std::vector<const uint8_t*> inst_ptr(B), proof_ptr(B);
+  std::vector<size_t> plen(B, proof_len);
+  for (size_t b = 0; b < B; b++) {
+    uint8_t* ie = inst.data() + b * (size_t)4 * ell * 48;
+    const uint8_t* pre = pre_trackers + b * (size_t)ell * 96;
+    const uint8_t* post = post_trackers + b * (size_t)ell * 96;
+    for (uint32_t i = 0; i < ell; i++) {
+      memcpy(ie + (size_t)i * 48, pre + 96 * i, 48);
+      memcpy(ie + ((size_t)ell + i) * 48, pre + 96 * i + 48, 48);
+      memcpy(ie + ((size_t)2 * ell + i) * 48, post + 96 * i, 48);
+      memcpy(ie + ((size_t)3 * ell + i) * 48, post + 96 * i + 48, 48);
+    }
+    inst_ptr[b] = ie;
+    proof_ptr[b] = proofs + b * proof_len;
+  }
+  std::vector<Engine::ParsedProof> pp;
+  if ((rc = load_proofs(E, L, (uint32_t)B, proof_ptr.data(), plen.data(), true, nullptr, inst_ptr, true, pp))) return rc;
+  std::vector<cdl_rand*> rands(rands_in, rands_in + B);
+  std::vector<int32_t> verdict, status;
+  std::vector<std::string> errs;
+  // decode failures are the reference's (false, err) with a decode error
+  std::vector<uint8_t> decode_failed(B, 0);
+  for (size_t b = 0; b < B; b++) decode_failed[b] = !pp[b].ok;
+  if ((rc = E->verify(L, (uint32_t)B, crs, pp, rands, verdict, status, errs))) return rc;
+  for (size_t b = 0; b < B; b++) {
+    ok[b] = verdict[b];
+    status_out[b] = decode_failed[b] ? CDL_ERR_DECODE : status[b];
+    if (status_out[b] != CDL_OK) { ok[b] = 0; c->fail(status_out[b], "%s", errs[b].c_str()); }
+  }
+  return CDL_OK;
+}
+
+int32_t cdl_whisk_is_valid_shuffle_proof(cdl_ctx* c, const cdl_crs* crs, const uint8_t* pre_trackers,
+                                         const uint8_t* post_trackers, size_t n_pre, size_t n_post,
+                                         const uint8_t* proof, size_t proof_len, cdl_rand* r, int32_t* ok) {
+  if (!c || !crs || !ok) return CDL_ERR_INVALID_ARG;
+  *ok = 0;
+  if (n_pre != n_post) return c->fail(CDL_ERR_PROTOCOL, "pre and post shuffle trackers must be the same length");
+  if (n_pre != crs->ell) return c->fail(CDL_ERR_INVALID_ARG, "tracker count %zu does not match the CRS (ell = %u)", n_pre, crs->ell);
+  int32_t status = CDL_OK;
+  cdl_rand* rr[1] = {r};
+  int32_t rc = cdl_whisk_is_valid_shuffle_proof_batch(c, crs, 1, pre_trackers, post_trackers, proof, proof_len, rr, ok, &status);
+  if (rc) return rc;
+  return status;
+}
+
+}  // extern "C"

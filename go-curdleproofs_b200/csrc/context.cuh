@@ -8,13 +8,6 @@
 
 #include "../../include/curdle_b200.h"
 
-namespace cdl {
-__global__ void k_iota(uint32_t* out, uint32_t n) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = i;
-}
-}  // namespace cdl
-
 struct cdl_ctx {
   int device = 0;
   int sm_count = 0;
@@ -24,6 +17,7 @@ struct cdl_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::mutex mu;
   std::string err;
+  void* engine = nullptr;  // cdlh::Engine, created on first protocol-level call
   static constexpr int kSlots = 8;
   void* slot[kSlots] = {};
   size_t cap[kSlots] = {};

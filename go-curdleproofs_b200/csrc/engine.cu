@@ -1,0 +1,831 @@
+// Batched curdleproofs engine — see host/engine.hpp.
+#include "host/engine.hpp"
+
+#include <algorithm>
+#include <array>
+#include <cstring>
+
+using cdl::ElemOp;
+using cdl::G1Affine;
+using cdl::MsmTask;
+
+namespace cdlh {
+
+static const uint8_t kInfEnc[48] = {0xc0};
+
+Layout::Layout(uint32_t ell_) {
+  ell = ell_;
+  n = ell + kBlinders;
+  m = 0;
+  while ((1u << m) < n) m++;
+  Gs = 0; Hs = ell; H = ell + 4; Gt = ell + 5; Gu = ell + 6; Gsum = ell + 7; Hsum = ell + 8; INF = ell + 9;
+  crs_size = ell + 10;
+  uint32_t o = 0;
+  Rs = o; o += ell;
+  Ss = o; o += ell;
+  Ts = o; o += ell;
+  Us = o; o += ell;
+  M = o++; A = o++; B = o++;
+  scratch = o; o += kScratch;
+  G = o; o += n;
+  Gp = o; o += n;
+  Gm = o; o += n;
+  Tp = o; o += n;
+  Up = o; o += n;
+  PP = o; o += 19 + 10 * 32;  // room for the largest accepted proof (lg n < 32)
+  inst_size = o;
+}
+
+// ------------------------------------------------------------------ plumbing
+Engine::Engine(cdl_ctx* ctx) : ctx_(ctx), pool_(std::max(1u, std::min(64u, std::thread::hardware_concurrency()))) {}
+
+Engine::~Engine() {
+  cudaSetDevice(ctx_->device);
+  if (d_pool_) cudaFree(d_pool_);
+  for (Staging* s : {&s_idx_, &s_sc_, &s_task_, &s_out_, &s_ops_, &s_enc_, &s_st_, &s_jac_}) {
+    if (s->h) cudaFreeHost(s->h);
+    if (s->d) cudaFree(s->d);
+  }
+}
+
+int32_t Engine::reserve(Staging& s, size_t bytes) {
+  if (bytes <= s.cap) return CDL_OK;
+  cudaStreamSynchronize(ctx_->stream);
+  if (s.h) cudaFreeHost(s.h);
+  if (s.d) cudaFree(s.d);
+  s.h = s.d = nullptr;
+  s.cap = 0;
+  size_t want = bytes + bytes / 2 + 256;
+  if (cudaMallocHost(&s.h, want) != cudaSuccess || cudaMalloc(&s.d, want) != cudaSuccess)
+    return ctx_->fail(CDL_ERR_CUDA, "engine staging allocation of %zu bytes failed", want);
+  s.cap = want;
+  return CDL_OK;
+}
+
+int32_t Engine::ensure_pool(size_t npoints) {
+  if (npoints <= pool_cap_) return CDL_OK;
+  cudaStreamSynchronize(ctx_->stream);
+  if (d_pool_) cudaFree(d_pool_);
+  d_pool_ = nullptr;
+  pool_cap_ = 0;
+  size_t want = npoints + npoints / 4;
+  if (cudaMalloc(&d_pool_, want * sizeof(G1Affine)) != cudaSuccess)
+    return ctx_->fail(CDL_ERR_CUDA, "point pool allocation of %zu points failed", want);
+  pool_cap_ = want;
+  return CDL_OK;
+}
+
+int32_t Engine::load_crs(const Layout& L, const cdl_crs* crs) {
+  CDL_CUDA(ctx_, cudaMemcpyAsync(d_pool_, crs->d_points, (size_t)L.crs_size * sizeof(G1Affine),
+                                 cudaMemcpyDeviceToDevice, ctx_->stream));
+  return CDL_OK;
+}
+
+int32_t Engine::upload_points(uint32_t dst, const void* host_affine, size_t count) {
+  if (!count) return CDL_OK;
+  CDL_CUDA(ctx_, cudaMemcpyAsync(d_pool_ + dst, host_affine, count * sizeof(G1Affine), cudaMemcpyHostToDevice, ctx_->stream));
+  CDL_CUDA(ctx_, cudaStreamSynchronize(ctx_->stream));  // caller memory is pageable and may go away
+  return CDL_OK;
+}
+
+int32_t Engine::upload_jac(uint32_t dst, const void* host_jac, size_t count) {
+  if (!count) return CDL_OK;
+  int32_t rc = reserve(s_jac_, count * sizeof(cdl::G1Jac));
+  if (rc) return rc;
+  memcpy(s_jac_.h, host_jac, count * sizeof(cdl::G1Jac));
+  CDL_CUDA(ctx_, cudaMemcpyAsync(s_jac_.d, s_jac_.h, count * sizeof(cdl::G1Jac), cudaMemcpyHostToDevice, ctx_->stream));
+  cdl::launch_jac_to_affine((const cdl::G1Jac*)s_jac_.d, d_pool_ + dst, (int)count, ctx_->stream);
+  launches++;
+  CDL_CUDA(ctx_, cudaGetLastError());
+  CDL_CUDA(ctx_, cudaStreamSynchronize(ctx_->stream));
+  return CDL_OK;
+}
+
+int32_t Engine::download_points(uint32_t src, void* host_affine, size_t count) {
+  if (!count) return CDL_OK;
+  CDL_CUDA(ctx_, cudaMemcpyAsync(host_affine, d_pool_ + src, count * sizeof(G1Affine), cudaMemcpyDeviceToHost, ctx_->stream));
+  CDL_CUDA(ctx_, cudaStreamSynchronize(ctx_->stream));
+  return CDL_OK;
+}
+
+int32_t Engine::copy_points(uint32_t dst, uint32_t src, size_t count) {
+  if (!count) return CDL_OK;
+  CDL_CUDA(ctx_, cudaMemcpyAsync(d_pool_ + dst, d_pool_ + src, count * sizeof(G1Affine), cudaMemcpyDeviceToDevice, ctx_->stream));
+  return CDL_OK;
+}
+
+int32_t Engine::set_infinity(uint32_t dst, size_t count) {
+  if (!count) return CDL_OK;
+  CDL_CUDA(ctx_, cudaMemsetAsync(d_pool_ + dst, 0, count * sizeof(G1Affine), ctx_->stream));
+  return CDL_OK;
+}
+
+int32_t Engine::compress(const std::vector<uint32_t>& src, std::vector<uint8_t>& out48) {
+  size_t n = src.size();
+  out48.resize(n * 48);
+  if (!n) return CDL_OK;
+  int32_t rc;
+  if ((rc = reserve(s_idx_, n * 4)) || (rc = reserve(s_out_, n * 48))) return rc;
+  memcpy(s_idx_.h, src.data(), n * 4);
+  CDL_CUDA(ctx_, cudaMemcpyAsync(s_idx_.d, s_idx_.h, n * 4, cudaMemcpyHostToDevice, ctx_->stream));
+  cdl::launch_compress_idx(d_pool_, (const uint32_t*)s_idx_.d, (uint8_t*)s_out_.d, (int)n, ctx_->stream);
+  launches++;
+  CDL_CUDA(ctx_, cudaGetLastError());
+  CDL_CUDA(ctx_, cudaMemcpyAsync(s_out_.h, s_out_.d, n * 48, cudaMemcpyDeviceToHost, ctx_->stream));
+  CDL_CUDA(ctx_, cudaStreamSynchronize(ctx_->stream));
+  memcpy(out48.data(), s_out_.h, n * 48);
+  return CDL_OK;
+}
+
+int32_t Engine::decompress(const uint8_t* enc48, const std::vector<uint32_t>& dst, std::vector<uint8_t>& status) {
+  size_t n = dst.size();
+  status.assign(n, 0);
+  if (!n) return CDL_OK;
+  int32_t rc;
+  if ((rc = reserve(s_idx_, n * 4)) || (rc = reserve(s_enc_, n * 48)) || (rc = reserve(s_st_, n))) return rc;
+  memcpy(s_idx_.h, dst.data(), n * 4);
+  memcpy(s_enc_.h, enc48, n * 48);
+  CDL_CUDA(ctx_, cudaMemcpyAsync(s_idx_.d, s_idx_.h, n * 4, cudaMemcpyHostToDevice, ctx_->stream));
+  CDL_CUDA(ctx_, cudaMemcpyAsync(s_enc_.d, s_enc_.h, n * 48, cudaMemcpyHostToDevice, ctx_->stream));
+  cdl::launch_decompress_idx((const uint8_t*)s_enc_.d, d_pool_, (const uint32_t*)s_idx_.d, (uint8_t*)s_st_.d, (int)n, ctx_->stream);
+  launches++;
+  CDL_CUDA(ctx_, cudaGetLastError());
+  CDL_CUDA(ctx_, cudaMemcpyAsync(s_st_.h, s_st_.d, n, cudaMemcpyDeviceToHost, ctx_->stream));
+  CDL_CUDA(ctx_, cudaStreamSynchronize(ctx_->stream));
+  memcpy(status.data(), s_st_.h, n);
+  return CDL_OK;
+}
+
+int32_t Engine::run_msm(MsmStage& st) {
+  size_t nt = st.tasks.size(), nterm = st.idx.size();
+  st.out48.resize(nt * 48);
+  if (!nt) return CDL_OK;
+  size_t max_terms = 0;
+  for (auto& t : st.tasks) max_terms = std::max<size_t>(max_terms, t.term_cnt);
+  if (max_terms > cdl::kMsmMaxTerms)
+    return ctx_->fail(CDL_ERR_TOO_LARGE, "msm of %zu terms exceeds the small-MSM limit %zu", max_terms, (size_t)cdl::kMsmMaxTerms);
+  int32_t rc;
+  if ((rc = reserve(s_idx_, (nterm + 1) * 4)) || (rc = reserve(s_sc_, (nterm + 1) * 32)) ||
+      (rc = reserve(s_task_, nt * sizeof(MsmTask))) || (rc = reserve(s_out_, nt * 48)))
+    return rc;
+  memcpy(s_idx_.h, st.idx.data(), nterm * 4);
+  memcpy(s_sc_.h, st.sc.data(), nterm * 32);
+  memcpy(s_task_.h, st.tasks.data(), nt * sizeof(MsmTask));
+  CDL_CUDA(ctx_, cudaMemcpyAsync(s_idx_.d, s_idx_.h, nterm * 4, cudaMemcpyHostToDevice, ctx_->stream));
+  CDL_CUDA(ctx_, cudaMemcpyAsync(s_sc_.d, s_sc_.h, nterm * 32, cudaMemcpyHostToDevice, ctx_->stream));
+  CDL_CUDA(ctx_, cudaMemcpyAsync(s_task_.d, s_task_.h, nt * sizeof(MsmTask), cudaMemcpyHostToDevice, ctx_->stream));
+  cdl::launch_msm_small(d_pool_, (const uint32_t*)s_idx_.d, (const cdl::Fr*)s_sc_.d, (const MsmTask*)s_task_.d, (int)nt,
+                        max_terms, d_pool_, (uint8_t*)s_out_.d, ctx_->stream);
+  launches++;
+  CDL_CUDA(ctx_, cudaGetLastError());
+  CDL_CUDA(ctx_, cudaMemcpyAsync(s_out_.h, s_out_.d, nt * 48, cudaMemcpyDeviceToHost, ctx_->stream));
+  CDL_CUDA(ctx_, cudaStreamSynchronize(ctx_->stream));
+  memcpy(st.out48.data(), s_out_.h, nt * 48);
+  return CDL_OK;
+}
+
+int32_t Engine::run_elem(const std::vector<ElemOp>& ops, const std::vector<Fr>& sc) {
+  size_t n = ops.size();
+  if (!n) return CDL_OK;
+  int32_t rc;
+  if ((rc = reserve(s_ops_, n * sizeof(ElemOp))) || (rc = reserve(s_sc_, sc.size() * 32))) return rc;
+  memcpy(s_ops_.h, ops.data(), n * sizeof(ElemOp));
+  memcpy(s_sc_.h, sc.data(), sc.size() * 32);
+  CDL_CUDA(ctx_, cudaMemcpyAsync(s_ops_.d, s_ops_.h, n * sizeof(ElemOp), cudaMemcpyHostToDevice, ctx_->stream));
+  CDL_CUDA(ctx_, cudaMemcpyAsync(s_sc_.d, s_sc_.h, sc.size() * 32, cudaMemcpyHostToDevice, ctx_->stream));
+  cdl::launch_elem_ops(d_pool_, (const ElemOp*)s_ops_.d, (const cdl::Fr*)s_sc_.d, (int)n, ctx_->stream);
+  launches++;
+  CDL_CUDA(ctx_, cudaGetLastError());
+  CDL_CUDA(ctx_, cudaStreamSynchronize(ctx_->stream));
+  return CDL_OK;
+}
+
+// ------------------------------------------------------------------ helpers
+namespace {
+
+// a stage with a fixed number of tasks/terms per instance; instance b builds
+// into its own slice, so the build parallelises over the batch
+struct StageBuilder {
+  MsmStage& st;
+  uint32_t B, terms_per, tasks_per;
+  StageBuilder(MsmStage& s, uint32_t B_, uint32_t terms, uint32_t tasks) : st(s), B(B_), terms_per(terms), tasks_per(tasks) {
+    st.idx.assign((size_t)B * terms, 0);
+    st.sc.assign((size_t)B * terms, FR_ZERO);
+    st.tasks.assign((size_t)B * tasks, MsmTask{0, 0, 0, 0});
+  }
+  MsmSlice slice(uint32_t b) {
+    MsmSlice s;
+    s.idx = st.idx.data() + (size_t)b * terms_per;
+    s.sc = st.sc.data() + (size_t)b * terms_per;
+    s.tasks = st.tasks.data() + (size_t)b * tasks_per;
+    s.term_base = b * terms_per;
+    return s;
+  }
+  // unused tail terms/tasks of an instance stay zero-length; compact before running
+  void compact() {
+    // tasks with term_cnt == 0 and out_idx == 0 that were never begun are dropped only when a
+    // whole instance was skipped (error state); keep the layout otherwise.
+  }
+  const uint8_t* out(uint32_t b, uint32_t task) const { return st.out48.data() + ((size_t)b * tasks_per + task) * 48; }
+};
+
+inline bool is_inf_enc(const uint8_t* e) { return memcmp(e, kInfEnc, 48) == 0; }
+
+}  // namespace
+
+// ------------------------------------------------------------------ ShufflePermuteCommit
+int32_t Engine::shuffle_permute_commit(const Layout& L, uint32_t B, const std::vector<std::vector<uint32_t>>& perms,
+                                       const std::vector<Fr>& ks, std::vector<cdl_rand*>& rands,
+                                       std::vector<std::vector<Fr>>& rs_m) {
+  const uint32_t ell = L.ell;
+  // Ts[i] = k * Rs[perm[i]], Us[i] = k * Ss[perm[i]]   (common/util.go:55-66)
+  std::vector<ElemOp> ops((size_t)B * 2 * ell);
+  std::vector<Fr> sc(B);
+  for (uint32_t b = 0; b < B; b++) {
+    uint32_t base = L.base(b);
+    sc[b] = ks[b];
+    for (uint32_t i = 0; i < ell; i++) {
+      ops[(size_t)b * 2 * ell + i] = ElemOp{base + L.Rs + perms[b][i], cdl::kNoPoint, base + L.Ts + i, b};
+      ops[(size_t)b * 2 * ell + ell + i] = ElemOp{base + L.Ss + perms[b][i], cdl::kNoPoint, base + L.Us + i, b};
+    }
+  }
+  int32_t rc = run_elem(ops, sc);
+  if (rc) return rc;
+  // M = <perm(0..ell-1), Gs> + <rs_m, Hs>   (common/util.go:68-85)
+  MsmStage st;
+  StageBuilder sb(st, B, ell + kBlinders, 1);
+  rs_m.assign(B, std::vector<Fr>(kBlinders));
+  for (uint32_t b = 0; b < B; b++) {
+    rands[b]->r.get_frs(rs_m[b].data(), kBlinders);
+    MsmSlice s = sb.slice(b);
+    s.begin(L.base(b) + L.M);
+    for (uint32_t i = 0; i < ell; i++) s.term(L.Gs + i, fr_from_u64(perms[b][i]));
+    for (uint32_t j = 0; j < kBlinders; j++) s.term(L.Hs + j, rs_m[b][j]);
+    s.end();
+  }
+  return run_msm(st);
+}
+
+// ------------------------------------------------------------------ Prove
+namespace {
+
+struct ProveState {
+  Transcript tr{"curdleproofs"};
+  bool failed = false;
+  std::string err;
+  std::vector<Fr> as, perm_as, rs_a, bs, rs_b, cs, ds, r_cs, x, r;
+  Fr alpha, beta, p, r_p, z, r_t, r_u, r_a, r_b, r_k, z_k, z_t, z_u;
+  Fr beta_ipa;
+  // wire pieces (48-byte encodings)
+  uint8_t A[48], T1[48], T2[48], U1[48], U2[48], R[48], S[48], Bp[48], C[48], B_c[48], B_d[48];
+  uint8_t A1[48], A2[48], B1[48], B2[48], B_a[48], B_t[48], B_u[48];
+  std::vector<uint8_t> L_C, R_C, L_D, R_D, L_A, L_T, L_U, R_A, R_T, R_U;
+  Fr c0, d0, x0;
+  void fail(const std::string& e) { if (!failed) { failed = true; err = e; } }
+};
+
+// innerproductargument.go:299-391
+bool generate_ipa_blinders(Rand& rand, const std::vector<Fr>& cs, const std::vector<Fr>& ds, std::vector<Fr>& rs,
+                           std::vector<Fr>& zs, std::string& err) {
+  size_t n = cs.size();
+  rs.resize(n);
+  zs.resize(n - 2);
+  rand.get_frs(rs.data(), n);
+  rand.get_frs(zs.data(), n - 2);
+  Fr omega = fr_add(fr_inner(rs.data(), ds.data(), n), fr_inner(zs.data(), cs.data(), n - 2));
+  Fr delta = fr_inner(rs.data(), zs.data(), n - 2);
+  Fr inv_c = fr_inv(cs[n - 2]);
+  Fr t1 = fr_sub(fr_mul(fr_mul(rs[n - 2], inv_c), omega), delta);
+  Fr t2 = fr_add(fr_mul(fr_mul(fr_neg(rs[n - 2]), inv_c), cs[n - 1]), rs[n - 1]);
+  if (fr_is_zero(t2)) { err = "last_z_term2 is zero"; return false; }
+  Fr last_z = fr_mul(t1, fr_inv(t2));
+  Fr pen_z = fr_mul(fr_neg(inv_c), fr_add(fr_mul(last_z, cs[n - 1]), omega));
+  zs.push_back(pen_z);
+  zs.push_back(last_z);
+  Fr chk = fr_add(fr_inner(rs.data(), ds.data(), n), fr_inner(zs.data(), cs.data(), n));
+  if (!fr_is_zero(chk) || !fr_is_zero(fr_inner(rs.data(), zs.data(), n))) {
+    err = "failed to generate IPA blinders: constraints not satisfied";
+    return false;
+  }
+  return true;
+}
+
+void put_u32_be(std::vector<uint8_t>& v, uint32_t x) {
+  v.push_back((uint8_t)(x >> 24)); v.push_back((uint8_t)(x >> 16)); v.push_back((uint8_t)(x >> 8)); v.push_back((uint8_t)x);
+}
+void put_pt(std::vector<uint8_t>& v, const uint8_t* e) { v.insert(v.end(), e, e + 48); }
+void put_slice(std::vector<uint8_t>& v, const std::vector<uint8_t>& pts) {
+  put_u32_be(v, (uint32_t)(pts.size() / 48));
+  v.insert(v.end(), pts.begin(), pts.end());
+}
+void put_fr(std::vector<uint8_t>& v, const Fr& s) {
+  uint8_t b[32];
+  fr_to_bytes_be(b, s);
+  v.insert(v.end(), b, b + 32);
+}
+
+}  // namespace
+
+int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std::vector<std::vector<uint32_t>>& perms,
+                      const std::vector<Fr>& ks, const std::vector<std::vector<Fr>>& rs_m_in,
+                      std::vector<cdl_rand*>& rands, std::vector<std::vector<uint8_t>>& proofs,
+                      std::vector<int32_t>& status, std::vector<std::string>& errs, std::vector<uint8_t>& inst_enc) {
+  const uint32_t ell = L.ell, n = L.n, m = L.m;
+  if (n != (1u << m)) return ctx_->fail(CDL_ERR_PROTOCOL, "cs and ds are not a power of two (ell + 4 = %u)", n);
+  int32_t rc;
+  std::vector<std::unique_ptr<ProveState>> S(B);
+  for (auto& s : S) s.reset(new ProveState());
+  const uint8_t* H_enc = crs->enc.data() + 48 * (size_t)L.H;
+  MsmStage st;
+
+  // ---- step 1: transcript over the instance (curdleproof.go:50-58)
+  std::vector<uint32_t> src;
+  src.reserve((size_t)B * (4 * ell + 1));
+  for (uint32_t b = 0; b < B; b++) {
+    uint32_t base = L.base(b);
+    for (uint32_t i = 0; i < 4 * ell; i++) src.push_back(base + L.Rs + i);  // Rs, Ss, Ts, Us are contiguous
+    src.push_back(base + L.M);
+  }
+  if ((rc = compress(src, inst_enc))) return rc;
+  const size_t per_inst = (size_t)(4 * ell + 1) * 48;
+  pool_.parallel_for(B, [&](size_t b) {
+    ProveState& s = *S[b];
+    const uint8_t* e = inst_enc.data() + b * per_inst;
+    s.tr.append_points("curdleproofs_step1", e, 4 * ell + 1);
+    s.as.resize(ell);
+    for (uint32_t i = 0; i < ell; i++) s.as[i] = s.tr.challenge("curdleproofs_vec_a");
+    s.rs_a.resize(kBlinders - 2);
+    rands[b]->r.get_frs(s.rs_a.data(), kBlinders - 2);  // :61
+    s.perm_as.resize(ell);
+    for (uint32_t i = 0; i < ell; i++) s.perm_as[i] = s.as[perms[b][i]];
+  });
+
+  // ---- A = <perm_as, Gs> + <rs_a', Hs>   (:72-79)
+  {
+    StageBuilder sb(st, B, ell + 2, 1);
+    pool_.parallel_for(B, [&](size_t b) {
+      ProveState& s = *S[b];
+      MsmSlice sl = sb.slice((uint32_t)b);
+      sl.begin(L.base((uint32_t)b) + L.A);
+      for (uint32_t i = 0; i < ell; i++) sl.term(L.Gs + i, s.perm_as[i]);
+      for (uint32_t j = 0; j < 2; j++) sl.term(L.Hs + j, s.rs_a[j]);
+      sl.end();
+    });
+    if ((rc = run_msm(st))) return rc;
+    for (uint32_t b = 0; b < B; b++) memcpy(S[b]->A, sb.out(b, 0), 48);
+  }
+
+  // ---- same-permutation argument, step 1-2 (samepermutationargument.go:44-80)
+  pool_.parallel_for(B, [&](size_t b) {
+    ProveState& s = *S[b];
+    const uint8_t* M_enc = inst_enc.data() + b * per_inst + (size_t)4 * ell * 48;
+    s.tr.append_points("same_perm_step1", s.A, 1);
+    s.tr.append_points("same_perm_step1", M_enc, 1);
+    s.tr.append_scalars("same_perm_step1", s.as.data(), ell);
+    s.alpha = s.tr.challenge("same_perm_alpha");
+    s.beta = s.tr.challenge("same_perm_beta");
+    s.bs.resize(ell);
+    s.p = FR_ONE;
+    for (uint32_t i = 0; i < ell; i++) {
+      s.bs[i] = fr_add(fr_add(fr_mul(s.alpha, fr_from_u64(perms[b][i])), s.perm_as[i]), s.beta);
+      s.p = fr_mul(s.p, s.bs[i]);
+    }
+    s.rs_b.resize(kBlinders);
+    for (uint32_t i = 0; i < kBlinders; i++) {
+      Fr ra = i < 2 ? s.rs_a[i] : FR_ZERO;
+      s.rs_b[i] = fr_add(fr_mul(s.alpha, rs_m_in[b][i]), ra);
+    }
+  });
+  // B = A + alpha*M + beta*sum(Gs)   (:62-73; sum(Gs) is crs.Gsum)
+  {
+    StageBuilder sb(st, B, 3, 1);
+    for (uint32_t b = 0; b < B; b++) {
+      ProveState& s = *S[b];
+      MsmSlice sl = sb.slice(b);
+      uint32_t base = L.base(b);
+      sl.begin(base + L.B);
+      sl.term(base + L.A, FR_ONE);
+      sl.term(base + L.M, s.alpha);
+      sl.term(L.Gsum, s.beta);
+      sl.end();
+    }
+    if ((rc = run_msm(st))) return rc;
+    for (uint32_t b = 0; b < B; b++) memcpy(S[b]->Bp, sb.out(b, 0), 48);
+  }
+
+  // ---- grand-product argument (grandproductargument.go:52-92)
+  std::vector<Fr> gp_alpha(B), gp_beta(B);
+  pool_.parallel_for(B, [&](size_t b) {
+    ProveState& s = *S[b];
+    s.tr.append_points("gprod_step1", s.Bp, 1);
+    s.tr.append_scalar("gprod_step1", s.p);
+    gp_alpha[b] = s.tr.challenge("gprod_alpha");
+    s.cs.assign(ell, FR_ONE);
+    for (uint32_t i = 1; i < ell; i++) s.cs[i] = fr_mul(s.cs[i - 1], s.bs[i - 1]);
+    s.r_cs.resize(kBlinders);
+    rands[b]->r.get_frs(s.r_cs.data(), kBlinders);
+  });
+  {
+    StageBuilder sb(st, B, n, 1);
+    pool_.parallel_for(B, [&](size_t b) {
+      ProveState& s = *S[b];
+      MsmSlice sl = sb.slice((uint32_t)b);
+      sl.begin(L.base((uint32_t)b) + L.scratch);
+      for (uint32_t i = 0; i < ell; i++) sl.term(L.Gs + i, s.cs[i]);
+      for (uint32_t j = 0; j < kBlinders; j++) sl.term(L.Hs + j, s.r_cs[j]);
+      sl.end();
+    });
+    if ((rc = run_msm(st))) return rc;
+    for (uint32_t b = 0; b < B; b++) memcpy(S[b]->C, sb.out(b, 0), 48);
+  }
+  std::vector<std::vector<Fr>> r_b_plus_alpha(B), beta_pows(B);
+  std::vector<Fr> beta_l1(B);
+  {
+    // Gs'[i] = beta^-(i+1) Gs[i], Hs'[i] = beta^-(ell+1) Hs[i]  (:94-103) -> Gp; G = Gs || Hs
+    std::vector<ElemOp> ops((size_t)B * n);
+    std::vector<Fr> sc((size_t)B * (ell + 1));
+    pool_.parallel_for(B, [&](size_t b) {
+      ProveState& s = *S[b];
+      r_b_plus_alpha[b].resize(kBlinders);
+      for (uint32_t i = 0; i < kBlinders; i++) r_b_plus_alpha[b][i] = fr_add(s.rs_b[i], gp_alpha[b]);
+      s.r_p = fr_inner(r_b_plus_alpha[b].data(), s.r_cs.data(), kBlinders);
+      s.tr.append_points("gprod_step2", s.C, 1);
+      s.tr.append_scalar("gprod_step2", s.r_p);
+      gp_beta[b] = s.tr.challenge("gprod_beta");
+      if (fr_is_zero(gp_beta[b])) { s.fail("beta is zero"); }
+      Fr beta_inv = fr_inv(gp_beta[b]);
+      uint32_t base = L.base((uint32_t)b);
+      Fr t = beta_inv;
+      Fr* scb = sc.data() + b * (ell + 1);
+      for (uint32_t i = 0; i < ell; i++) {
+        scb[i] = t;
+        ops[b * n + i] = ElemOp{L.Gs + i, cdl::kNoPoint, base + L.Gp + i, (uint32_t)(b * (ell + 1) + i)};
+        t = fr_mul(t, beta_inv);
+      }
+      scb[ell] = t;
+      for (uint32_t j = 0; j < kBlinders; j++)
+        ops[b * n + ell + j] = ElemOp{L.Hs + j, cdl::kNoPoint, base + L.Gp + ell + j, (uint32_t)(b * (ell + 1) + ell)};
+    });
+    if ((rc = run_elem(ops, sc))) return rc;
+    for (uint32_t b = 0; b < B; b++)
+      if ((rc = copy_points(L.base(b) + L.G, L.Gs, n))) return rc;  // Gs and Hs are adjacent in the CRS image
+  }
+  // D, the two self-checks, B_c, B_d  (:105-177, innerproductargument.go:59-72)
+  std::vector<std::vector<Fr>> rs_c(B), rs_d(B);
+  std::vector<std::array<uint8_t, 48>> D_enc(B);
+  {
+    StageBuilder sb(st, B, 5 * n + 1, 5);
+    pool_.parallel_for(B, [&](size_t b) {
+      ProveState& s = *S[b];
+      const Fr& beta = gp_beta[b];
+      const Fr& alpha = gp_alpha[b];
+      // ds[i] = bs[i]*beta^(i+1) - beta^i ; betaPowers[i] = beta^i
+      s.ds.resize(ell);
+      beta_pows[b].resize(ell);
+      Fr tb = FR_ONE;
+      for (uint32_t i = 0; i < ell; i++) {
+        beta_pows[b][i] = tb;
+        Fr nx = fr_mul(tb, beta);
+        s.ds[i] = fr_sub(fr_mul(s.bs[i], nx), tb);
+        tb = nx;
+      }
+      Fr beta_l = tb;  // beta^ell
+      beta_l1[b] = fr_mul(beta_l, beta);
+      std::vector<Fr> r_ds(kBlinders);
+      for (uint32_t i = 0; i < kBlinders; i++) r_ds[i] = fr_mul(beta_l1[b], r_b_plus_alpha[b][i]);
+      Fr ab = fr_mul(alpha, beta_l1[b]);
+      s.z = fr_sub(fr_add(fr_mul(s.r_p, beta_l1[b]), fr_mul(s.p, beta_l)), FR_ONE);
+      s.cs.insert(s.cs.end(), s.r_cs.begin(), s.r_cs.end());
+      s.ds.insert(s.ds.end(), r_ds.begin(), r_ds.end());
+      if (!fr_eq(fr_inner(s.cs.data(), s.ds.data(), n), s.z)) s.fail("IPA(C, D) != z");
+      std::string e;
+      if (!s.failed && !generate_ipa_blinders(rands[b]->r, s.cs, s.ds, rs_c[b], rs_d[b], e)) s.fail("generate IPA blinders: " + e);
+      if (s.failed) { rs_c[b].assign(n, FR_ZERO); rs_d[b].assign(n, FR_ZERO); }
+      uint32_t base = L.base((uint32_t)b);
+      MsmSlice sl = sb.slice((uint32_t)b);
+      // D = B - <beta^i, Gs'> + <alpha*beta^(ell+1), Hs'>
+      sl.begin(base + L.scratch + 1);
+      sl.term(base + L.B, FR_ONE);
+      for (uint32_t i = 0; i < ell; i++) sl.term(base + L.Gp + i, fr_neg(beta_pows[b][i]));
+      for (uint32_t j = 0; j < kBlinders; j++) sl.term(base + L.Gp + ell + j, ab);
+      sl.end();
+      sl.begin(base + L.scratch + 2);  // msm(G, c) must equal C
+      for (uint32_t i = 0; i < n; i++) sl.term(base + L.G + i, s.cs[i]);
+      sl.end();
+      sl.begin(base + L.scratch + 3);  // msm(G', d) must equal D
+      for (uint32_t i = 0; i < n; i++) sl.term(base + L.Gp + i, s.ds[i]);
+      sl.end();
+      sl.begin(base + L.scratch + 4);  // B_c
+      for (uint32_t i = 0; i < n; i++) sl.term(base + L.G + i, rs_c[b][i]);
+      sl.end();
+      sl.begin(base + L.scratch + 5);  // B_d
+      for (uint32_t i = 0; i < n; i++) sl.term(base + L.Gp + i, rs_d[b][i]);
+      sl.end();
+    });
+    if ((rc = run_msm(st))) return rc;
+    for (uint32_t b = 0; b < B; b++) {
+      ProveState& s = *S[b];
+      memcpy(D_enc[b].data(), sb.out(b, 0), 48);
+      if (memcmp(sb.out(b, 1), s.C, 48) != 0) s.fail("msm(G, c) != C");
+      else if (memcmp(sb.out(b, 2), D_enc[b].data(), 48) != 0) s.fail("msm(G', d) != D");
+      memcpy(s.B_c, sb.out(b, 3), 48);
+      memcpy(s.B_d, sb.out(b, 4), 48);
+    }
+  }
+  // ---- inner-product argument (innerproductargument.go:74-188)
+  pool_.parallel_for(B, [&](size_t b) {
+    ProveState& s = *S[b];
+    s.tr.append_points("ipa_step1", s.C, 1);
+    s.tr.append_points("ipa_step1", D_enc[b].data(), 1);
+    s.tr.append_scalar("ipa_step1", s.z);
+    s.tr.append_points("ipa_step1", s.B_c, 1);
+    s.tr.append_points("ipa_step1", s.B_d, 1);
+    Fr alpha = s.tr.challenge("ipa_alpha");
+    s.beta_ipa = s.tr.challenge("ipa_beta");
+    for (uint32_t i = 0; i < n; i++) {
+      s.cs[i] = fr_add(rs_c[b][i], fr_mul(alpha, s.cs[i]));
+      s.ds[i] = fr_add(rs_d[b][i], fr_mul(alpha, s.ds[i]));
+    }
+  });
+  for (uint32_t half = n / 2; half >= 1; half /= 2) {
+    StageBuilder sb(st, B, 4 * half + 2, 4);
+    pool_.parallel_for(B, [&](size_t b) {
+      ProveState& s = *S[b];
+      uint32_t base = L.base((uint32_t)b);
+      const Fr *c_L = s.cs.data(), *c_R = s.cs.data() + half, *d_L = s.ds.data(), *d_R = s.ds.data() + half;
+      MsmSlice sl = sb.slice((uint32_t)b);
+      sl.begin(base + L.scratch);  // L_C = <c_L, G_R> + <c_L, d_R> * (beta*H)
+      for (uint32_t i = 0; i < half; i++) sl.term(base + L.G + half + i, c_L[i]);
+      sl.term(L.H, fr_mul(s.beta_ipa, fr_inner(c_L, d_R, half)));
+      sl.end();
+      sl.begin(base + L.scratch + 1);  // L_D = <d_R, G'_L>
+      for (uint32_t i = 0; i < half; i++) sl.term(base + L.Gp + i, d_R[i]);
+      sl.end();
+      sl.begin(base + L.scratch + 2);  // R_C = <c_R, G_L> + <c_R, d_L> * (beta*H)
+      for (uint32_t i = 0; i < half; i++) sl.term(base + L.G + i, c_R[i]);
+      sl.term(L.H, fr_mul(s.beta_ipa, fr_inner(c_R, d_L, half)));
+      sl.end();
+      sl.begin(base + L.scratch + 3);  // R_D = <d_L, G'_R>
+      for (uint32_t i = 0; i < half; i++) sl.term(base + L.Gp + half + i, d_L[i]);
+      sl.end();
+    });
+    if ((rc = run_msm(st))) return rc;
+    std::vector<ElemOp> ops(half > 1 ? (size_t)B * 2 * (half) : 0);
+    std::vector<Fr> sc((size_t)B * 2);
+    pool_.parallel_for(B, [&](size_t b) {
+      ProveState& s = *S[b];
+      const uint8_t *lc = sb.out((uint32_t)b, 0), *ld = sb.out((uint32_t)b, 1), *rcc = sb.out((uint32_t)b, 2), *rd = sb.out((uint32_t)b, 3);
+      s.L_C.insert(s.L_C.end(), lc, lc + 48);
+      s.L_D.insert(s.L_D.end(), ld, ld + 48);
+      s.R_C.insert(s.R_C.end(), rcc, rcc + 48);
+      s.R_D.insert(s.R_D.end(), rd, rd + 48);
+      s.tr.append_points("ipa_loop", lc, 1);
+      s.tr.append_points("ipa_loop", ld, 1);
+      s.tr.append_points("ipa_loop", rcc, 1);
+      s.tr.append_points("ipa_loop", rd, 1);
+      Fr gamma = s.tr.challenge("ipa_gamma");
+      if (fr_is_zero(gamma)) s.fail("ipa gamma challenge is zero");
+      Fr gamma_inv = fr_inv(gamma);
+      for (uint32_t i = 0; i < half; i++) {
+        s.cs[i] = fr_add(s.cs[i], fr_mul(gamma_inv, s.cs[half + i]));
+        s.ds[i] = fr_add(s.ds[i], fr_mul(gamma, s.ds[half + i]));
+      }
+      sc[2 * b] = gamma;
+      sc[2 * b + 1] = gamma_inv;
+      if (half > 1) {  // the folded bases of the last round are never read again
+        uint32_t base = L.base((uint32_t)b);
+        ElemOp* o = ops.data() + b * 2 * half;
+        for (uint32_t i = 0; i < half; i++) {
+          o[i] = ElemOp{base + L.G + half + i, base + L.G + i, base + L.G + i, (uint32_t)(2 * b)};
+          o[half + i] = ElemOp{base + L.Gp + half + i, base + L.Gp + i, base + L.Gp + i, (uint32_t)(2 * b + 1)};
+        }
+      }
+    });
+    if ((rc = run_elem(ops, sc))) return rc;
+  }
+  for (uint32_t b = 0; b < B; b++) { S[b]->c0 = S[b]->cs[0]; S[b]->d0 = S[b]->ds[0]; }
+
+  // ---- step 3: R, S, T, U, same-scalar commitments, A', B_a/B_t/B_u
+  // (curdleproof.go:101-122,146-148; samescalarargument.go:46-64; samemultiscalarargument.go:58-72)
+  {
+    const uint32_t terms = 6 * (ell + 1) + 4 + 3 + (n) + (ell + 1) + (ell + 1);
+    StageBuilder sb(st, B, terms, 14);
+    // working vectors of the same-multiscalar argument
+    for (uint32_t b = 0; b < B; b++) {
+      uint32_t base = L.base(b);
+      if ((rc = copy_points(base + L.Gm, L.Gs, ell + 2))) return rc;       // Gs || Hs[0..2)
+      if ((rc = copy_points(base + L.Gm + ell + 2, L.Gt, 2))) return rc;   // Gt, Gu
+      if ((rc = copy_points(base + L.Tp, base + L.Ts, ell))) return rc;
+      if ((rc = copy_points(base + L.Up, base + L.Us, ell))) return rc;
+      if ((rc = set_infinity(base + L.Tp + ell, 4))) return rc;
+      if ((rc = set_infinity(base + L.Up + ell, 4))) return rc;
+      if ((rc = copy_points(base + L.Tp + ell + 2, L.H, 1))) return rc;    // T' = Ts || 0 || 0 || H || 0
+      if ((rc = copy_points(base + L.Up + ell + 3, L.H, 1))) return rc;    // U' = Us || 0 || 0 || 0 || H
+    }
+    pool_.parallel_for(B, [&](size_t b) {
+      ProveState& s = *S[b];
+      Rand& rand = rands[b]->r;
+      s.r_t = rand.get_fr();
+      s.r_u = rand.get_fr();
+      s.r_a = rand.get_fr();  // samescalarargument.go:46-57
+      s.r_b = rand.get_fr();
+      s.r_k = rand.get_fr();
+      s.r.resize(n);
+      rand.get_frs(s.r.data(), n);  // samemultiscalarargument.go:58
+      const Fr& k = ks[b];
+      uint32_t base = L.base((uint32_t)b);
+      MsmSlice sl = sb.slice((uint32_t)b);
+      uint32_t o = base + L.scratch;
+      auto lin = [&](uint32_t out, uint32_t pts, const Fr* mulby, uint32_t extra_pt, const Fr* extra_sc) {
+        sl.begin(out);
+        for (uint32_t i = 0; i < ell; i++) sl.term(base + pts + i, mulby ? fr_mul(*mulby, s.as[i]) : s.as[i]);
+        if (extra_sc) sl.term(extra_pt, *extra_sc);
+        sl.end();
+      };
+      lin(o + 0, L.Rs, nullptr, 0, nullptr);        // R = <as, Rs>
+      lin(o + 1, L.Ss, nullptr, 0, nullptr);        // S = <as, Ss>
+      sl.begin(o + 2); sl.term(L.Gt, s.r_t); sl.end();  // T_1 = r_t * Gt
+      lin(o + 3, L.Rs, &k, L.H, &s.r_t);            // T_2 = k*R + r_t*H
+      sl.begin(o + 4); sl.term(L.Gu, s.r_u); sl.end();  // U_1
+      lin(o + 5, L.Ss, &k, L.H, &s.r_u);            // U_2
+      sl.begin(o + 6); sl.term(L.Gt, s.r_a); sl.end();  // A_1 = r_a * Gt
+      lin(o + 7, L.Rs, &s.r_k, L.H, &s.r_a);        // A_2 = r_k*R + r_a*H
+      sl.begin(o + 8); sl.term(L.Gu, s.r_b); sl.end();  // B_1
+      lin(o + 9, L.Ss, &s.r_k, L.H, &s.r_b);        // B_2
+      sl.begin(o + 10);                              // A' = A + T_1 + U_1
+      sl.term(base + L.A, FR_ONE); sl.term(L.Gt, s.r_t); sl.term(L.Gu, s.r_u);
+      sl.end();
+      sl.begin(o + 11);                              // B_a = <r, G>
+      for (uint32_t i = 0; i < n; i++) sl.term(base + L.Gm + i, s.r[i]);
+      sl.end();
+      sl.begin(o + 12);                              // B_t = <r, T'>
+      for (uint32_t i = 0; i < ell; i++) sl.term(base + L.Ts + i, s.r[i]);
+      sl.term(L.H, s.r[ell + 2]);
+      sl.end();
+      sl.begin(o + 13);                              // B_u = <r, U'>
+      for (uint32_t i = 0; i < ell; i++) sl.term(base + L.Us + i, s.r[i]);
+      sl.term(L.H, s.r[ell + 3]);
+      sl.end();
+    });
+    if ((rc = run_msm(st))) return rc;
+    pool_.parallel_for(B, [&](size_t b) {
+      ProveState& s = *S[b];
+      auto out = [&](uint32_t t) { return sb.out((uint32_t)b, t); };
+      memcpy(s.R, out(0), 48); memcpy(s.S, out(1), 48);
+      memcpy(s.T1, out(2), 48); memcpy(s.T2, out(3), 48); memcpy(s.U1, out(4), 48); memcpy(s.U2, out(5), 48);
+      memcpy(s.A1, out(6), 48); memcpy(s.A2, out(7), 48); memcpy(s.B1, out(8), 48); memcpy(s.B2, out(9), 48);
+      memcpy(s.B_a, out(11), 48); memcpy(s.B_t, out(12), 48); memcpy(s.B_u, out(13), 48);
+      // same-scalar argument transcript (samescalarargument.go:66-80)
+      const uint8_t* seq[10] = {s.R, s.S, s.T1, s.T2, s.U1, s.U2, s.A1, s.A2, s.B1, s.B2};
+      for (auto e : seq) s.tr.append_points("sameexp_points", e, 1);
+      Fr a = s.tr.challenge("sameexp_alpha");
+      s.z_k = fr_add(s.r_k, fr_mul(ks[b], a));
+      s.z_t = fr_add(s.r_a, fr_mul(s.r_t, a));
+      s.z_u = fr_add(s.r_b, fr_mul(s.r_u, a));
+      // same-multiscalar argument, step 1 (samemultiscalarargument.go:74-83)
+      const uint8_t* ie = inst_enc.data() + b * per_inst;
+      s.tr.append_points("same_msm_step1", out(10), 1);
+      s.tr.append_points("same_msm_step1", s.T2, 1);
+      s.tr.append_points("same_msm_step1", s.U2, 1);
+      s.tr.append_points("same_msm_step1", ie + (size_t)2 * ell * 48, ell);  // Ts
+      s.tr.append_points("same_msm_step1", kInfEnc, 1);
+      s.tr.append_points("same_msm_step1", kInfEnc, 1);
+      s.tr.append_points("same_msm_step1", H_enc, 1);
+      s.tr.append_points("same_msm_step1", kInfEnc, 1);
+      s.tr.append_points("same_msm_step1", ie + (size_t)3 * ell * 48, ell);  // Us
+      s.tr.append_points("same_msm_step1", kInfEnc, 1);
+      s.tr.append_points("same_msm_step1", kInfEnc, 1);
+      s.tr.append_points("same_msm_step1", kInfEnc, 1);
+      s.tr.append_points("same_msm_step1", H_enc, 1);
+      s.tr.append_points("same_msm_step1", s.B_a, 1);
+      s.tr.append_points("same_msm_step1", s.B_t, 1);
+      s.tr.append_points("same_msm_step1", s.B_u, 1);
+      Fr alpha = s.tr.challenge("same_msm_alpha");
+      // x = perm_as || rs_a || r_t || r_u ; x = r + alpha*x   (curdleproof.go:167-170, :80-83)
+      s.x.resize(n);
+      for (uint32_t i = 0; i < ell; i++) s.x[i] = s.perm_as[i];
+      s.x[ell] = s.rs_a[0]; s.x[ell + 1] = s.rs_a[1]; s.x[ell + 2] = s.r_t; s.x[ell + 3] = s.r_u;
+      for (uint32_t i = 0; i < n; i++) s.x[i] = fr_add(s.r[i], fr_mul(s.x[i], alpha));
+    });
+  }
+  // ---- same-multiscalar rounds (samemultiscalarargument.go:85-140)
+  for (uint32_t half = n / 2; half >= 1; half /= 2) {
+    StageBuilder sb(st, B, 6 * half, 6);
+    pool_.parallel_for(B, [&](size_t b) {
+      ProveState& s = *S[b];
+      uint32_t base = L.base((uint32_t)b);
+      const Fr *x_L = s.x.data(), *x_R = s.x.data() + half;
+      MsmSlice sl = sb.slice((uint32_t)b);
+      const uint32_t vec[3] = {L.Gm, L.Tp, L.Up};
+      for (int v = 0; v < 3; v++) {  // L_A, L_T, L_U over the right halves with x_L
+        sl.begin(base + L.scratch + v);
+        for (uint32_t i = 0; i < half; i++) sl.term(base + vec[v] + half + i, x_L[i]);
+        sl.end();
+      }
+      for (int v = 0; v < 3; v++) {  // R_A, R_T, R_U over the left halves with x_R
+        sl.begin(base + L.scratch + 3 + v);
+        for (uint32_t i = 0; i < half; i++) sl.term(base + vec[v] + i, x_R[i]);
+        sl.end();
+      }
+    });
+    if ((rc = run_msm(st))) return rc;
+    std::vector<ElemOp> ops(half > 1 ? (size_t)B * 3 * half : 0);
+    std::vector<Fr> sc(B);
+    pool_.parallel_for(B, [&](size_t b) {
+      ProveState& s = *S[b];
+      std::vector<uint8_t>* dstv[6] = {&s.L_A, &s.L_T, &s.L_U, &s.R_A, &s.R_T, &s.R_U};
+      for (int t = 0; t < 6; t++) {
+        const uint8_t* e = sb.out((uint32_t)b, t);
+        dstv[t]->insert(dstv[t]->end(), e, e + 48);
+        s.tr.append_points("same_msm_loop", e, 1);
+      }
+      Fr gamma = s.tr.challenge("same_msm_gamma");
+      if (fr_is_zero(gamma)) s.fail("gamma is zero");
+      Fr gamma_inv = fr_inv(gamma);
+      for (uint32_t i = 0; i < half; i++) s.x[i] = fr_add(s.x[i], fr_mul(gamma_inv, s.x[half + i]));
+      sc[b] = gamma;
+      if (half > 1) {
+        uint32_t base = L.base((uint32_t)b);
+        const uint32_t vec[3] = {L.Tp, L.Up, L.Gm};
+        ElemOp* o = ops.data() + b * 3 * half;
+        for (int v = 0; v < 3; v++)
+          for (uint32_t i = 0; i < half; i++)
+            o[v * half + i] = ElemOp{base + vec[v] + half + i, base + vec[v] + i, base + vec[v] + i, (uint32_t)b};
+      }
+    });
+    if ((rc = run_elem(ops, sc))) return rc;
+  }
+
+  // ---- serialize (curdleproof.go:358-387 and the sub-proof Serialize methods)
+  proofs.assign(B, {});
+  status.assign(B, CDL_OK);
+  errs.assign(B, "");
+  for (uint32_t b = 0; b < B; b++) {
+    ProveState& s = *S[b];
+    if (s.failed) { status[b] = CDL_ERR_PROTOCOL; errs[b] = s.err; continue; }
+    std::vector<uint8_t>& v = proofs[b];
+    put_pt(v, s.A); put_pt(v, s.T1); put_pt(v, s.T2); put_pt(v, s.U1); put_pt(v, s.U2); put_pt(v, s.R); put_pt(v, s.S);
+    put_pt(v, s.Bp);                      // same-permutation proof
+    put_pt(v, s.C); put_fr(v, s.r_p);     // grand-product proof
+    put_pt(v, s.B_c); put_pt(v, s.B_d);   // inner-product proof
+    put_slice(v, s.L_C); put_slice(v, s.R_C); put_slice(v, s.L_D); put_slice(v, s.R_D);
+    put_fr(v, s.c0); put_fr(v, s.d0);
+    put_pt(v, s.A1); put_pt(v, s.A2); put_pt(v, s.B1); put_pt(v, s.B2);  // same-scalar proof
+    put_fr(v, s.z_k); put_fr(v, s.z_t); put_fr(v, s.z_u);
+    put_pt(v, s.B_a); put_pt(v, s.B_t); put_pt(v, s.B_u);                // same-multiscalar proof
+    put_slice(v, s.L_A); put_slice(v, s.L_T); put_slice(v, s.L_U);
+    put_slice(v, s.R_A); put_slice(v, s.R_T); put_slice(v, s.R_U);
+    put_fr(v, s.x[0]);
+  }
+  return CDL_OK;
+}
+
+// ------------------------------------------------------------------ wire walker
+std::string parse_wire_proof(const uint8_t* buf, size_t len, bool with_m, WireProof& out, size_t* used) {
+  size_t pos = 0;
+  out.points.clear();
+  int nsc = 0, nlen = 0;
+  auto point = [&]() -> const char* {
+    if (pos + 48 > len) return "unexpected EOF";
+    uint8_t f = buf[pos] & 0xe0;
+    if (f == 0xe0 || f == 0x60 || f == 0x20) return "invalid encoding";
+    if (!(f & 0x80)) return "uncompressed point encodings are not supported by this build";
+    out.points.push_back(buf + pos);
+    pos += 48;
+    return nullptr;
+  };
+  auto slice = [&]() -> const char* {
+    if (pos + 4 > len) return "unexpected EOF";
+    uint32_t c = ((uint32_t)buf[pos] << 24) | ((uint32_t)buf[pos + 1] << 16) | ((uint32_t)buf[pos + 2] << 8) | buf[pos + 3];
+    pos += 4;
+    if ((size_t)c * 48 > len - pos) return "unexpected EOF";
+    out.lens[nlen++] = c;
+    for (uint32_t i = 0; i < c; i++)
+      if (const char* e = point()) return e;
+    return nullptr;
+  };
+  auto scalar = [&]() -> const char* {
+    if (pos + 32 > len) return "unexpected EOF";
+    out.scalars[nsc++] = buf + pos;
+    pos += 32;
+    return nullptr;
+  };
+#define CDL_TRY(x) do { if (const char* e__ = (x)) return e__; } while (0)
+  if (with_m) CDL_TRY(point());
+  for (int i = 0; i < 7; i++) CDL_TRY(point());  // A, T_1, T_2, U_1, U_2, R, S
+  CDL_TRY(point());                               // B
+  CDL_TRY(point()); CDL_TRY(scalar());            // C, Rp
+  CDL_TRY(point()); CDL_TRY(point());             // B_c, B_d
+  for (int i = 0; i < 4; i++) CDL_TRY(slice());   // L_Cs, R_Cs, L_Ds, R_Ds
+  CDL_TRY(scalar()); CDL_TRY(scalar());           // c0, d0
+  for (int i = 0; i < 4; i++) CDL_TRY(point());   // A_1, A_2, B_1, B_2
+  for (int i = 0; i < 3; i++) CDL_TRY(scalar());  // Z_k, Z_t, Z_u
+  for (int i = 0; i < 3; i++) CDL_TRY(point());   // B_a, B_t, B_u
+  for (int i = 0; i < 6; i++) CDL_TRY(slice());   // L_A, L_T, L_U, R_A, R_T, R_U
+  CDL_TRY(scalar());                              // x
+#undef CDL_TRY
+  if (used) *used = pos;
+  return "";
+}
+
+}  // namespace cdlh

@@ -1,0 +1,174 @@
+// Host-side scalar field Fr of BLS12-381 (4 x 64-bit Montgomery limbs) — the
+// part of gnark-crypto's fr.Element the reference's *host* code uses between GPU
+// calls: challenge arithmetic, vector folding of cs/ds/x, inner products, powers
+// of beta, verifier scalar unfolding (e.g. innerproductargument.go:80-88,
+// 155-158, 223-234; grandproductargument.go:57-129; common/util.go:26-35).
+// Same memory layout as fr.Element, so values upload to the device unchanged.
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+namespace cdlh {
+
+typedef unsigned __int128 u128;
+
+struct Fr {
+  uint64_t l[4];
+};
+
+static const uint64_t FR_MOD[4] = {0xffffffff00000001ull, 0x53bda402fffe5bfeull, 0x3339d80809a1d805ull,
+                                   0x73eda753299d7d48ull};
+static const uint64_t FR_INV = 0xfffffffeffffffffull;  // -r^-1 mod 2^64
+static const Fr FR_ONE = {{0x00000001fffffffeull, 0x5884b7fa00034802ull, 0x998c4fefecbc4ff5ull, 0x1824b159acc5056full}};
+static const Fr FR_R2 = {{0xc999e990f3f29c6dull, 0x2b6cedcb87925c23ull, 0x05d314967254398full, 0x0748d9d99f59ff11ull}};
+static const Fr FR_ZERO = {{0, 0, 0, 0}};
+
+inline bool fr_is_zero(const Fr& a) { return (a.l[0] | a.l[1] | a.l[2] | a.l[3]) == 0; }
+inline bool fr_eq(const Fr& a, const Fr& b) { return memcmp(a.l, b.l, 32) == 0; }
+
+inline bool fr_geq_mod(const uint64_t* a) {
+  for (int i = 3; i >= 0; i--) {
+    if (a[i] > FR_MOD[i]) return true;
+    if (a[i] < FR_MOD[i]) return false;
+  }
+  return true;
+}
+inline void fr_sub_mod(uint64_t* a) {
+  uint64_t b = 0;
+  for (int i = 0; i < 4; i++) {
+    u128 t = (u128)a[i] - FR_MOD[i] - b;
+    a[i] = (uint64_t)t;
+    b = (uint64_t)(t >> 64) & 1;
+  }
+}
+inline Fr fr_add(const Fr& a, const Fr& b) {
+  Fr r;
+  uint64_t c = 0;
+  for (int i = 0; i < 4; i++) {
+    u128 t = (u128)a.l[i] + b.l[i] + c;
+    r.l[i] = (uint64_t)t;
+    c = (uint64_t)(t >> 64);
+  }
+  if (c || fr_geq_mod(r.l)) fr_sub_mod(r.l);
+  return r;
+}
+inline Fr fr_sub(const Fr& a, const Fr& b) {
+  Fr r;
+  uint64_t bw = 0;
+  for (int i = 0; i < 4; i++) {
+    u128 t = (u128)a.l[i] - b.l[i] - bw;
+    r.l[i] = (uint64_t)t;
+    bw = (uint64_t)(t >> 64) & 1;
+  }
+  if (bw) {
+    uint64_t c = 0;
+    for (int i = 0; i < 4; i++) {
+      u128 t = (u128)r.l[i] + FR_MOD[i] + c;
+      r.l[i] = (uint64_t)t;
+      c = (uint64_t)(t >> 64);
+    }
+  }
+  return r;
+}
+inline Fr fr_neg(const Fr& a) { return fr_is_zero(a) ? a : fr_sub(FR_ZERO, a); }
+
+inline Fr fr_mul(const Fr& a, const Fr& b) {
+  uint64_t t[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < 4; i++) {
+    u128 c = 0;
+    for (int j = 0; j < 4; j++) {
+      c += (u128)a.l[j] * b.l[i] + t[j];
+      t[j] = (uint64_t)c;
+      c >>= 64;
+    }
+    c += t[4];
+    t[4] = (uint64_t)c;
+    t[5] = (uint64_t)(c >> 64);
+    uint64_t m = t[0] * FR_INV;
+    c = (u128)m * FR_MOD[0] + t[0];
+    c >>= 64;
+    for (int j = 1; j < 4; j++) {
+      c += (u128)m * FR_MOD[j] + t[j];
+      t[j - 1] = (uint64_t)c;
+      c >>= 64;
+    }
+    c += t[4];
+    t[3] = (uint64_t)c;
+    t[4] = t[5] + (uint64_t)(c >> 64);
+  }
+  Fr r = {{t[0], t[1], t[2], t[3]}};
+  if (t[4] || fr_geq_mod(r.l)) fr_sub_mod(r.l);
+  return r;
+}
+inline Fr fr_sqr(const Fr& a) { return fr_mul(a, a); }
+
+inline Fr fr_from_u64(uint64_t v) {  // fr.NewElement
+  Fr c = {{v, 0, 0, 0}};
+  return fr_mul(c, FR_R2);
+}
+inline Fr fr_from_canonical(const uint64_t* w) {
+  Fr c = {{w[0], w[1], w[2], w[3]}};
+  return fr_mul(c, FR_R2);
+}
+inline void fr_to_canonical(uint64_t* w, const Fr& a) {
+  Fr one = {{1, 0, 0, 0}};
+  Fr c = fr_mul(a, one);
+  memcpy(w, c.l, 32);
+}
+// fr.Element.Bytes(): 32-byte big-endian canonical
+inline void fr_to_bytes_be(uint8_t* out, const Fr& a) {
+  uint64_t w[4];
+  fr_to_canonical(w, a);
+  for (int i = 0; i < 4; i++)
+    for (int k = 0; k < 8; k++) out[8 * i + k] = (uint8_t)(w[3 - i] >> (56 - 8 * k));
+}
+// fr.Element.SetBytesCanonical: false when the value is >= r
+inline bool fr_from_bytes_be_canonical(Fr& r, const uint8_t* in) {
+  uint64_t w[4];
+  for (int i = 0; i < 4; i++) {
+    uint64_t v = 0;
+    for (int k = 0; k < 8; k++) v = (v << 8) | in[8 * i + k];
+    w[3 - i] = v;
+  }
+  if (fr_geq_mod(w)) return false;
+  r = fr_from_canonical(w);
+  return true;
+}
+inline Fr fr_pow_u64(const Fr& a, uint64_t e) {  // fr.Element.Exp with a small exponent
+  Fr acc = FR_ONE, base = a;
+  while (e) {
+    if (e & 1) acc = fr_mul(acc, base);
+    base = fr_sqr(base);
+    e >>= 1;
+  }
+  return acc;
+}
+// fr.Element.Inverse: a^(r-2); Inverse(0) = 0
+inline Fr fr_inv(const Fr& a) {
+  uint64_t e[4] = {FR_MOD[0] - 2, FR_MOD[1], FR_MOD[2], FR_MOD[3]};
+  Fr acc = FR_ONE;
+  bool started = false;
+  for (int w = 3; w >= 0; w--)
+    for (int bit = 63; bit >= 0; bit--) {
+      if (started) acc = fr_sqr(acc);
+      if ((e[w] >> bit) & 1) {
+        if (started) acc = fr_mul(acc, a); else { acc = a; started = true; }
+      }
+    }
+  return acc;
+}
+// fr.BatchInvert: zeros stay zero
+inline std::vector<Fr> fr_batch_inv(const std::vector<Fr>& v) {
+  std::vector<Fr> out(v.size());
+  for (size_t i = 0; i < v.size(); i++) out[i] = fr_inv(v[i]);
+  return out;
+}
+// common.IPA (common/util.go:26-35)
+inline Fr fr_inner(const Fr* a, const Fr* b, size_t n) {
+  Fr acc = FR_ZERO;
+  for (size_t i = 0; i < n; i++) acc = fr_add(acc, fr_mul(a[i], b[i]));
+  return acc;
+}
+
+}  // namespace cdlh

@@ -41,6 +41,35 @@ k_jac_to_affine(const G1Jac* __restrict__ in, G1Affine* __restrict__ out, int n)
 }
 
 
+// Descriptor-driven form used by the protocol engine: every op reads and writes
+// the device-resident point pool, so folded bases never leave HBM between
+// rounds (the reference mutates its slices in place the same way,
+// innerproductargument.go:157-171).  A launch never has dst aliasing another
+// op's src/add, so ops are independent.
+__global__ void __launch_bounds__(128)
+k_elem_ops(G1Affine* __restrict__ pool, const ElemOp* __restrict__ ops, const Fr* __restrict__ scalars, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  ElemOp op = ops[i];
+  Fr km = scalars[op.sc], k;
+  FrM::from_mont(k, km);
+  G1Affine p = pool[op.src];
+  G1Jac r;
+  jac_scalar_mul(r, p, k.v);
+  if (op.add != kNoPoint) {
+    G1Affine l = pool[op.add];
+    jac_add_mixed(r, r, l);
+  }
+  G1Affine a;
+  jac_to_affine(a, r);
+  pool[op.dst] = a;
+}
+
+void launch_elem_ops(G1Affine* pool, const ElemOp* ops, const Fr* scalars, int n, cudaStream_t st) {
+  const int tpb = 64;
+  k_elem_ops<<<(n + tpb - 1) / tpb, tpb, 0, st>>>(pool, ops, scalars, n);
+}
+
 void launch_scalar_mul(const G1Affine* P, const Fr* s, int stride, const G1Affine* L, G1Affine* out, int n,
                        cudaStream_t st) {
   const int tpb = 64;

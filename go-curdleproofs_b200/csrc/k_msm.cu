@@ -163,7 +163,7 @@ k_msm_small(const G1Affine* __restrict__ points, const uint32_t* __restrict__ id
   if (tid == 0) {
     G1Affine a;
     jac_to_affine(a, win[0]);
-    if (out_aff) out_aff[blockIdx.x] = a;
+    if (out_aff) out_aff[task.out_idx] = a;
     if (out_c48) g1_compress_dev(out_c48 + 48 * (size_t)blockIdx.x, a);
   }
 }

@@ -111,6 +111,85 @@ int32_t cdl_g1_compress(cdl_ctx* ctx, const cdl_g1_affine* in, size_t n, uint8_t
  * 5 bad infinity padding).  Returns CDL_ERR_DECODE if any point failed. */
 int32_t cdl_g1_decompress(cdl_ctx* ctx, const uint8_t* in48, size_t n, cdl_g1_affine* out, uint8_t* status);
 
+/* ---- protocol level: the reference's public API, batched on the GPU ------
+ * The Go types with unexported fields (curdleproof.Proof, whisk.*Bytes) cross
+ * this boundary in their own wire format (curdleproof.go:358-387,
+ * whisk/types.go:53-72); INTEGRATION.md shows the Go-side wrappers.  Group
+ * elements never touch the host except as 48-byte encodings; the host side of
+ * these calls is the Merlin transcript, Fiat-Shamir challenges, Fr arithmetic
+ * and the RNG, exactly the split north_star describes.                        */
+
+typedef struct cdl_rand cdl_rand; /* common.Rand (common/rand.go:13-33) */
+typedef struct cdl_crs cdl_crs;   /* curdleproof.CRS (crs.go:10-18), device resident */
+
+#define CDL_N_BLINDERS 4                    /* common/constants.go:3 */
+#define CDL_WHISK_SHUFFLE_PROOF_SIZE 4576   /* whisk/types.go:21 */
+#define CDL_WHISK_TRACKER_SIZE 96           /* WhiskTracker{rG, krG}: 2 x 48 B, whisk/types.go:74-77 */
+
+/* common.NewRand / GetFr(s) / GetG1Affines / GeneratePermutation (common/rand.go:19-113) */
+int32_t cdl_rand_new(uint64_t seed, cdl_rand** out);
+void cdl_rand_free(cdl_rand* r);
+int32_t cdl_rand_get_frs(cdl_rand* r, size_t n, cdl_fr* out);
+int32_t cdl_rand_get_g1_affines(cdl_ctx* ctx, cdl_rand* r, size_t n, cdl_g1_affine* out);
+int32_t cdl_rand_generate_permutation(cdl_rand* r, size_t n, uint32_t* out);
+
+/* curdleproof.GenerateCRS (crs.go:20-59): draws ell Gs, 4 Hs, H, Gt, Gu and forms Gsum, Hsum. */
+int32_t cdl_crs_generate(cdl_ctx* ctx, size_t ell, cdl_rand* r, cdl_crs** out);
+/* Wrap an existing Go-side CRS: points[] = Gs[ell] | Hs[4] | H | Gt | Gu | Gsum | Hsum, all affine. */
+int32_t cdl_crs_from_points(cdl_ctx* ctx, size_t ell, const cdl_g1_affine* points, cdl_crs** out);
+/* Same order as cdl_crs_from_points, ell + 9 points. */
+int32_t cdl_crs_export(cdl_ctx* ctx, const cdl_crs* crs, cdl_g1_affine* points);
+size_t cdl_crs_ell(const cdl_crs* crs);
+void cdl_crs_free(cdl_crs* crs);
+
+/* common.ShufflePermuteCommit (common/util.go:45-88): Ts = perm(k*Rs), Us = perm(k*Ss),
+ * M = <perm(0..ell-1), Gs> + <rs_m, Hs> with rs_m = 4 fresh Fr from r. */
+int32_t cdl_shuffle_permute_commit(cdl_ctx* ctx, const cdl_crs* crs, const cdl_g1_affine* Rs, const cdl_g1_affine* Ss,
+                                   const uint32_t* perm, const cdl_fr* k, cdl_rand* r, cdl_g1_affine* Ts,
+                                   cdl_g1_affine* Us, cdl_g1_jac* M, cdl_fr* rs_m);
+
+/* curdleproof.Prove (curdleproof.go:38-197) followed by Proof.Serialize (:358-387).
+ * proof_len receives the serialized size (18 + 10m points, 7 scalars, 10 length prefixes). */
+int32_t cdl_prove(cdl_ctx* ctx, const cdl_crs* crs, const cdl_g1_affine* Rs, const cdl_g1_affine* Ss,
+                  const cdl_g1_affine* Ts, const cdl_g1_affine* Us, const cdl_g1_jac* M, const uint32_t* perm,
+                  const cdl_fr* k, const cdl_fr* rs_m, cdl_rand* r, uint8_t* proof, size_t proof_cap,
+                  size_t* proof_len);
+
+/* Proof.FromReader (curdleproof.go:320-356) + curdleproof.Verify (:199-318).
+ * *ok = 1 / 0 is the reference's bool; a non-zero return is the reference's error
+ * (CDL_ERR_DECODE for malformed bytes, CDL_ERR_PROTOCOL e.g. "randomizer is zero"). */
+int32_t cdl_verify(cdl_ctx* ctx, const cdl_crs* crs, const uint8_t* proof, size_t proof_len,
+                   const cdl_g1_affine* Rs, const cdl_g1_affine* Ss, const cdl_g1_affine* Ts,
+                   const cdl_g1_affine* Us, const cdl_g1_jac* M, cdl_rand* r, int32_t* ok);
+
+/* whisk.GenerateWhiskShuffleProof (whisk/whisk.go:63-114).  Trackers are
+ * 96-byte {rG, krG} pairs; crs ell trackers in, ell out; proof is zero padded
+ * to proof_cap (4576 for the reference's N = 128). */
+int32_t cdl_whisk_generate_shuffle_proof(cdl_ctx* ctx, const cdl_crs* crs, const uint8_t* pre_trackers,
+                                         cdl_rand* r, uint8_t* post_trackers, uint8_t* proof, size_t proof_cap);
+/* whisk.IsValidWhiskShuffleProof (whisk/whisk.go:20-61). */
+int32_t cdl_whisk_is_valid_shuffle_proof(cdl_ctx* ctx, const cdl_crs* crs, const uint8_t* pre_trackers,
+                                         const uint8_t* post_trackers, size_t n_pre, size_t n_post,
+                                         const uint8_t* proof, size_t proof_len, cdl_rand* r, int32_t* ok);
+
+/* Batched forms: B independent instances advance in lock step, one GPU launch
+ * per protocol stage for the whole batch (config 4 of BASELINE.json).  Arrays
+ * are instance-major; status[b] is the per-instance return code. */
+int32_t cdl_whisk_generate_shuffle_proof_batch(cdl_ctx* ctx, const cdl_crs* crs, size_t B,
+                                               const uint8_t* pre_trackers, cdl_rand* const* rands,
+                                               uint8_t* post_trackers, uint8_t* proofs, size_t proof_cap,
+                                               int32_t* status);
+int32_t cdl_whisk_is_valid_shuffle_proof_batch(cdl_ctx* ctx, const cdl_crs* crs, size_t B,
+                                               const uint8_t* pre_trackers, const uint8_t* post_trackers,
+                                               const uint8_t* proofs, size_t proof_len, cdl_rand* const* rands,
+                                               int32_t* ok, int32_t* status);
+/* Host-side self test (no GPU needed): out32 receives Merlin's published
+ * "test protocol" challenge computed by the library's transcript code;
+ * fr_out receives (a*b + a - b)^-1 * a^5 computed by the host Fr code. */
+int32_t cdl_host_selftest(uint8_t* out32, const cdl_fr* a, const cdl_fr* b, cdl_fr* fr_out);
+/* Number of GPU kernels launched by protocol-level calls on this context so far. */
+uint64_t cdl_launch_count(cdl_ctx* ctx);
+
 /* ---- diagnostics / roofline ------------------------------------------- */
 /* out[i] = a[i] * b[i] in Fp (Montgomery).  K1 of SURVEY.md §7. */
 int32_t cdl_fp_mul(cdl_ctx* ctx, const cdl_fp* a, const cdl_fp* b, size_t n, cdl_fp* out);

@@ -370,6 +370,36 @@ def g1_decompress(buf: bytes, subgroup_check: bool = True):
     return pt
 
 
+# Optional accelerated batch decompressor (set by oracle.cbackend): takes n*48
+# bytes of *compressed* encodings, returns (points, status codes).
+_decompress_batch = None
+
+
+def set_decompress_batch(fn) -> None:
+    global _decompress_batch
+    _decompress_batch = fn
+
+
+_REASONS = {1: "invalid encoding", 2: "non-canonical coordinate",
+            3: "invalid compressed coordinate: square root doesn't exist",
+            4: "invalid point: subgroup check failed", 5: "invalid infinity encoding"}
+
+
+def g1_decompress_many(encs):
+    """SetBytes on a list of 48-byte compressed encodings (whisk/types.go:86-95);
+    raises DecodeError for the first bad one."""
+    if _decompress_batch is None:
+        return [g1_decompress(e) for e in encs]
+    for e in encs:
+        if len(e) != G1_COMPRESSED:
+            raise DecodeError("short buffer")
+    pts, st = _decompress_batch(b"".join(encs))
+    for code in st:
+        if code:
+            raise DecodeError(_REASONS.get(code, "decode error"))
+    return pts
+
+
 class Encoder:
     """bls12381.NewEncoder(w): compressed points, 32-byte BE scalars, uint32-BE
     slice-length prefix (assumed, unpinned — SURVEY.md §8c-i)."""
@@ -413,6 +443,8 @@ class Decoder:
             raise DecodeError("invalid encoding")
         if m in (M_UNCOMPRESSED, M_UNCOMPRESSED_INF):
             head = head + self._take(G1_COMPRESSED)
+        elif _decompress_batch is not None:
+            return g1_decompress_many([head])[0]
         pt, _ = g1_set_bytes(head)
         return pt
 
@@ -420,6 +452,23 @@ class Decoder:
         n = int.from_bytes(self._take(4), "big")
         if n * G1_COMPRESSED > len(self.data) - self.pos:
             raise DecodeError("unexpected EOF")
+        if _decompress_batch is not None:
+            # gnark decodes slice elements first and validates them afterwards;
+            # either way any bad element fails the whole Decode.
+            heads = []
+            for _ in range(n):
+                h = self._take(G1_COMPRESSED)
+                m = h[0] & M_MASK
+                if m in (0b111 << 5, 0b011 << 5, 0b001 << 5):
+                    raise DecodeError("invalid encoding")
+                if m in (M_UNCOMPRESSED, M_UNCOMPRESSED_INF):
+                    pt, _ = g1_set_bytes(h + self._take(G1_COMPRESSED))
+                    heads.append(pt)
+                else:
+                    heads.append(h)
+            comp = [h for h in heads if isinstance(h, (bytes, bytearray))]
+            dec = iter(g1_decompress_many(comp))
+            return [next(dec) if isinstance(h, (bytes, bytearray)) else h for h in heads]
         return [self.point() for _ in range(n)]
 
     def scalar(self) -> int:

@@ -93,33 +93,47 @@ static void fp_neg(fp* r, const fp* a) {
   fp z = {{0}};
   fp_sub(r, &z, a);
 }
-/* Montgomery product, operand scanning (CIOS) on 64-bit words */
+/* Montgomery product: operand-scanning CIOS on 64-bit words, fully unrolled and
+ * register resident.  p < 2^381 leaves the top word with spare bits, so the
+ * running sum never needs a 8th word ("no-carry" variant). */
+#define CO_MAC(lo, hi, x, y, add1, add2)                      \
+  do {                                                        \
+    u128 t__ = (u128)(x) * (y) + (add1) + (add2);             \
+    (lo) = (uint64_t)t__;                                     \
+    (hi) = (uint64_t)(t__ >> 64);                             \
+  } while (0)
+#define CO_ROW(bi_)                                           \
+  do {                                                        \
+    uint64_t bi = (bi_), c, m, d, junk;                       \
+    CO_MAC(t0, c, a0, bi, t0, 0);                             \
+    CO_MAC(t1, c, a1, bi, t1, c);                             \
+    CO_MAC(t2, c, a2, bi, t2, c);                             \
+    CO_MAC(t3, c, a3, bi, t3, c);                             \
+    CO_MAC(t4, c, a4, bi, t4, c);                             \
+    CO_MAC(t5, c, a5, bi, t5, c);                             \
+    t6 = c;                                                   \
+    m = t0 * FP_INV;                                          \
+    CO_MAC(junk, d, m, p0, t0, 0);                            \
+    (void)junk;                                               \
+    CO_MAC(t0, d, m, p1, t1, d);                              \
+    CO_MAC(t1, d, m, p2, t2, d);                              \
+    CO_MAC(t2, d, m, p3, t3, d);                              \
+    CO_MAC(t3, d, m, p4, t4, d);                              \
+    CO_MAC(t4, d, m, p5, t5, d);                              \
+    t5 = t6 + d;                                              \
+  } while (0)
 static void fp_mul(fp* r, const fp* a, const fp* b) {
-  uint64_t t[8] = {0};
-  for (int i = 0; i < 6; i++) {
-    u128 c = 0;
-    for (int j = 0; j < 6; j++) {
-      c += (u128)a->l[j] * b->l[i] + t[j];
-      t[j] = (uint64_t)c;
-      c >>= 64;
-    }
-    c += t[6];
-    t[6] = (uint64_t)c;
-    t[7] = (uint64_t)(c >> 64);
-    uint64_t m = t[0] * FP_INV;
-    c = (u128)m * FP_P.l[0] + t[0];
-    c >>= 64;
-    for (int j = 1; j < 6; j++) {
-      c += (u128)m * FP_P.l[j] + t[j];
-      t[j - 1] = (uint64_t)c;
-      c >>= 64;
-    }
-    c += t[6];
-    t[5] = (uint64_t)c;
-    t[6] = t[7] + (uint64_t)(c >> 64);
-  }
-  for (int i = 0; i < 6; i++) r->l[i] = t[i];
-  if (t[6] || fp_geq_p(r)) fp_sub_p(r);
+  const uint64_t a0 = a->l[0], a1 = a->l[1], a2 = a->l[2], a3 = a->l[3], a4 = a->l[4], a5 = a->l[5];
+  const uint64_t p0 = FP_P.l[0], p1 = FP_P.l[1], p2 = FP_P.l[2], p3 = FP_P.l[3], p4 = FP_P.l[4], p5 = FP_P.l[5];
+  uint64_t t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0, t6 = 0;
+  CO_ROW(b->l[0]);
+  CO_ROW(b->l[1]);
+  CO_ROW(b->l[2]);
+  CO_ROW(b->l[3]);
+  CO_ROW(b->l[4]);
+  CO_ROW(b->l[5]);
+  r->l[0] = t0; r->l[1] = t1; r->l[2] = t2; r->l[3] = t3; r->l[4] = t4; r->l[5] = t5;
+  if (fp_geq_p(r)) fp_sub_p(r);
 }
 static void fp_sqr(fp* r, const fp* a) { fp_mul(r, a, a); }
 static void fp_pow(fp* r, const fp* a, const uint64_t* e, int nwords) {
@@ -231,10 +245,36 @@ static void jac_from_aff(jac* r, const aff* p) {
   if (aff_is_inf(p)) { jac_set_inf(r); return; }
   r->x = p->x; r->y = p->y; r->z = FP_ONE;
 }
+/* r = p + q, q affine (8M + 3S) */
 static void jac_add_aff(jac* r, const jac* p, const aff* q) {
-  jac t;
-  jac_from_aff(&t, q);
-  jac_add(r, p, &t);
+  if (aff_is_inf(q)) { *r = *p; return; }
+  if (jac_is_inf(p)) { jac_from_aff(r, q); return; }
+  fp z1z1, u2, s2, h, rr, hh, hhh, v, t;
+  fp_sqr(&z1z1, &p->z);
+  fp_mul(&u2, &q->x, &z1z1);
+  fp_mul(&s2, &q->y, &p->z);
+  fp_mul(&s2, &s2, &z1z1);
+  if (fp_eq(&u2, &p->x)) {
+    if (fp_eq(&s2, &p->y)) { jac_dbl(r, p); return; }
+    jac_set_inf(r);
+    return;
+  }
+  fp_sub(&h, &u2, &p->x);
+  fp_sub(&rr, &s2, &p->y);
+  fp_sqr(&hh, &h);
+  fp_mul(&hhh, &hh, &h);
+  fp_mul(&v, &p->x, &hh);
+  fp x3, y3, z3;
+  fp_sqr(&x3, &rr);
+  fp_sub(&x3, &x3, &hhh);
+  fp_sub(&x3, &x3, &v);
+  fp_sub(&x3, &x3, &v);
+  fp_sub(&t, &v, &x3);
+  fp_mul(&y3, &rr, &t);
+  fp_mul(&t, &p->y, &hhh);
+  fp_sub(&y3, &y3, &t);
+  fp_mul(&z3, &p->z, &h);
+  r->x = x3; r->y = y3; r->z = z3;
 }
 /* batch Jacobian -> affine (Montgomery's trick) */
 static void jac_batch_to_aff(aff* out, const jac* in, size_t n) {

@@ -60,11 +60,11 @@ def generate_whisk_shuffle_proof(crs: proto.CRS, pre_trackers, rand: Rand, ell: 
     generalise the compile-time constants for the small test shapes."""
     perm = rand.generate_permutation(ell)
     k = rand.get_fr()
-    Rs, Ss = [], []
-    for t in pre_trackers:
-        r, s = tracker_points(t)
-        Rs.append(r)
-        Ss.append(s)
+    try:
+        flat = bls.g1_decompress_many([x for t in pre_trackers for x in t])
+    except bls.DecodeError as e:
+        raise WhiskError(f"getting points: {e}")
+    Rs, Ss = flat[0::2], flat[1::2]
     Ts, Us, M, rs_m = proto.shuffle_permute_commit(crs.Gs, crs.Hs, Rs, Ss, perm, k, rand)
     proof = proto.prove(crs, Rs, Ss, Ts, Us, M, perm, k, rs_m, rand)
     proof_bytes = serialize_shuffle_proof(M, proof, proof_size)
@@ -81,14 +81,11 @@ def is_valid_whisk_shuffle_proof(crs: proto.CRS, pre, post, proof_bytes: bytes, 
         M, proof = deserialize_shuffle_proof(proof_bytes)
     except bls.DecodeError as e:
         raise WhiskError(f"decoding proof: {e}")
-    Rs, Ss, Ts, Us = [], [], [], []
-    for i in range(len(pre)):
-        r, s = tracker_points(pre[i])
-        t, u = tracker_points(post[i])
-        Rs.append(r)
-        Ss.append(s)
-        Ts.append(t)
-        Us.append(u)
+    try:
+        flat = bls.g1_decompress_many([x for i in range(len(pre)) for x in (pre[i][0], pre[i][1], post[i][0], post[i][1])])
+    except bls.DecodeError as e:
+        raise WhiskError(f"getting shuffle points: {e}")
+    Rs, Ss, Ts, Us = flat[0::4], flat[1::4], flat[2::4], flat[3::4]
     return proto.verify(proof, crs, Rs, Ss, Ts, Us, M, rand)
 
 

@@ -1,0 +1,31 @@
+"""Host-side pieces of the product library that need no GPU: common.Rand,
+Merlin transcript, Fr arithmetic — checked against the oracle / public KATs."""
+import ctypes as C
+import random
+
+from oracle import bls12381 as b
+from oracle.rand import Rand as ORand
+from util import R, fr_dec, fr_enc
+
+
+def test_rand_matches_oracle(pkg):
+    for seed in (0, 42, 43, 2**63 + 5):
+        r = pkg.Rand(seed)
+        o = ORand(seed)
+        got = r.get_frs(40)
+        assert [fr_dec(got[i:i + 32]) for i in range(0, len(got), 32)] == o.get_frs(40)
+        assert r.generate_permutation(124) == o.generate_permutation(124)
+        assert fr_dec(r.get_fr()) == o.get_fr()
+
+
+def test_merlin_kat_and_fr(pkg):
+    lib = pkg.load_library()
+    random.seed(3)
+    for _ in range(20):
+        a, x = random.randrange(1, R), random.randrange(1, R)
+        out = C.create_string_buffer(32)
+        fr_out = C.create_string_buffer(32)
+        assert lib.cdl_host_selftest(out, fr_enc(a), fr_enc(x), fr_out) == 0
+        assert out.raw.hex() == "d5a21972d0d5fe320c0d263fac7fffb8145aa640af6e9bca177c03c7efcf0615"
+        want = b.fr_inv((a * x + a - x) % R) * pow(a, 5, R) % R
+        assert fr_dec(fr_out.raw) == want
