@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native G1 hot path.
+
+Workload (BASELINE.json configs[1]): Whisk shape, shuffled_elements = 124
+(n = 128): GenerateWhiskShuffleProof + IsValidWhiskShuffleProof round trips.
+One *step* = one batch of B independent round trips (synthetic trackers),
+driven through the C ABI (cdl_whisk_*_batch) with HOST buffers.
+
+  value      proofs/s counting only device time: B*K / sum of the CUDA-event
+             durations of every kernel the step launched (inputs resident in
+             HBM; the host's Fiat-Shamir work between launches excluded)
+  e2e.value  proofs/s wall clock through the C ABI, host<->device copies and the
+             host-side transcript work inside the timed region
+  roofline   the dominant kernel class against the integer-pipe peak
+             (IMAD.WIDE issue rate measured live / 300 multiply-adds per
+             381-bit Montgomery product), HBM GB/s secondary
+  cpu_baseline  the CPU oracle ("port": C 6x64 Montgomery restatement driven by
+             the Python protocol restatement) on the host cores
+
+`--impl reference` times that CPU path alone on all host cores.
+Multi-GPU: one process per GPU (torchrun), independent proofs sharded across
+ranks, no data-path collective (weak scaling); NCCL only for the barrier and the
+max-over-ranks time.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+ELL = 124
+METRIC = "whisk_shuffle_proof_roundtrips_per_s (GenerateWhiskShuffleProof + IsValidWhiskShuffleProof, n=128)"
+UNIT = "proofs/s"
+MODMUL_IMADS = 300.0  # 2*12^2 + 12 wide multiply-adds per 381-bit Montgomery product
+
+
+# ----------------------------------------------------------------------------- reference arm (CPU oracle)
+def _ref_worker(args):
+    """One worker: `count` Whisk round trips on the CPU oracle, returns seconds."""
+    seed, count = args
+    sys.path.insert(0, ROOT)
+    from oracle import protocol as P, whisk as W
+    from oracle.cbackend import CBackend
+    from oracle.rand import Rand
+
+    cb = CBackend(threads=1)
+    P.set_backend(cb)
+    rand = Rand(0, backend=cb)
+    crs = P.generate_crs(ELL, rand)
+    pre = W.generate_shuffle_trackers(Rand(1000 + seed, backend=cb), ELL)
+    t0 = time.perf_counter()
+    for i in range(count):
+        r = Rand(3000 + seed * 1000 + i, backend=cb)
+        post, proof = W.generate_whisk_shuffle_proof(crs, pre, r)
+        ok = W.is_valid_whisk_shuffle_proof(crs, pre, post, proof, r)
+        assert ok
+    return time.perf_counter() - t0
+
+
+def run_reference_sample(workers: int, per_worker: int):
+    import multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    t0 = time.perf_counter()
+    with ctx.Pool(workers) as pool:
+        pool.map(_ref_worker, [(w, per_worker) for w in range(workers)])
+    dt = time.perf_counter() - t0
+    return workers * per_worker, dt
+
+
+def reference_main(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, ROOT)
+    from oracle.cbackend import build as build_oracle
+
+    build_oracle()
+    cores = os.cpu_count() or 1
+    workers = cores
+    per_worker = 2
+    _ref_worker((999, 1))  # warm import / build, untimed
+    for _ in range(args.warmup):
+        run_reference_sample(workers, per_worker)
+    t = []
+    proofs = 0
+    for _ in range(args.steps):
+        n, dt = run_reference_sample(workers, per_worker)
+        proofs += n
+        t.append(dt)
+    total = sum(t)
+    value = proofs / total
+    sample = (f"{workers} worker processes x {per_worker} Whisk n=128 round trip(s) per step, pool start-up "
+              f"included; {args.steps} steps")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, args.steps),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 (6x64-bit Montgomery limbs)",
+        "data": "synthetic", "config": {"workload": "whisk_n128_roundtrip", "shuffled_elements": ELL,
+                                         "proofs_per_step": workers * per_worker},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- GPU arm
+class ClockSampler(threading.Thread):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm = [float(s[1]) for s in self.samples if len(s) > 2 and s[1].replace(".", "").isdigit()]
+        mx = [float(s[2]) for s in self.samples if len(s) > 2 and s[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            for k, nm in enumerate(names):
+                if len(s) > 5 + k and s[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+def make_trackers(ctx, pkg, ell: int, seeds):
+    """Synthetic pre-shuffle trackers (whisk_test.go generateShuffleTrackers): (r*G, k*r*G) compressed."""
+    from oracle import bls12381 as b  # constants only (generator coordinates)
+    from util import aff_enc
+
+    gen = aff_enc(b.G1_GEN)
+    out = []
+    for s in seeds:
+        r = pkg.Rand(s)
+        ks, rs = [], []
+        for _ in range(ell):
+            ks.append(r.get_fr())
+            rs.append(r.get_fr())
+        rG = ctx.g1_scalar_mul_affine(gen * ell, b"".join(rs), broadcast=False)
+        krG = ctx.g1_scalar_mul_affine(rG, b"".join(ks), broadcast=False)
+        e1, e2 = ctx.g1_compress(rG), ctx.g1_compress(krG)
+        out.append(b"".join(e1[48 * j:48 * j + 48] + e2[48 * j:48 * j + 48] for j in range(ell)))
+    return out
+
+
+def gpu_main(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    pkg = importlib.import_module("go-curdleproofs_b200")
+    ctx = pkg.Context(local)  # raises without a GPU / without the built library: no fallback
+    info = ctx.device_info()
+    B = args.batch
+    crs = ctx.generate_crs(ELL, pkg.Rand(0))
+    # a few distinct tracker sets, cycled over the batch (every instance still gets its own RNG stream)
+    base_sets = make_trackers(ctx, pkg, ELL, [1000 + rank * 7919 + i for i in range(min(B, 8))])
+    pre = b"".join(base_sets[i % len(base_sets)] for i in range(B))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")  # > 126 MB L2
+
+    # integer-pipe peak, measured live (burst): IMAD.WIDE/s over the whole chip
+    imad_wide_per_s, _ = ctx.int_peak(1, 4000)
+    peak_modmul = imad_wide_per_s / MODMUL_IMADS
+
+    step_no = [0]
+
+    def step():
+        flush.zero_()  # L2 flush between iterations
+        s = step_no[0]
+        step_no[0] += 1
+        rands = [pkg.Rand((rank << 40) | (s << 20) | i) for i in range(B)]
+        post, proofs, status = ctx.whisk_generate_shuffle_proof_batch(crs, pre, rands)
+        ok, st = ctx.whisk_is_valid_shuffle_proof_batch(crs, pre, post, proofs, rands)
+        return status, ok, st
+
+    for _ in range(args.warmup):
+        status, ok, st = step()
+        assert status == [0] * B and ok == [1] * B and st == [0] * B, "warm-up round trip failed"
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    ctx.engine_stats(reset=True)
+    l0 = ctx.launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        status, ok, st = step()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    barrier()
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+    assert status == [0] * B and ok == [1] * B and st == [0] * B, "timed round trip failed"
+    stats = ctx.engine_stats()
+    launches = ctx.launch_count() - l0
+    dev_ms = sum(v["ms"] for v in stats.values())
+
+    t = torch.tensor([wall, dev_ms / 1e3], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    wall_max, dev_max = float(t[0]), float(t[1])
+    total_proofs = world * B * args.steps
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        top = max(stats, key=lambda k: stats[k]["ms"])
+        tk = stats[top]
+        n_launch = max(1, tk["launches"])
+        avg_ms = tk["ms"] / n_launch
+        achieved = tk["modmul"] / (tk["ms"] * 1e-3) if tk["ms"] else 0.0
+        roofline = {
+            "bound": "int_alu", "kernel": top, "achieved": achieved / 1e9, "peak": peak_modmul / 1e9,
+            "unit": "Gmodmul/s", "frac": achieved / peak_modmul if peak_modmul else None, "traffic": None,
+            "peak_source": "measured live: IMAD.WIDE.U32 issue rate (cdl_int_peak kind 1, burst) / 300 per modmul",
+            "avg_launch_ms": avg_ms, "launches": tk["launches"],
+            "algorithmic_modmul_per_launch": tk["modmul"] / n_launch,
+            "hbm": {"achieved_gbs": tk["bytes"] / (tk["ms"] * 1e-3) / 1e9 if tk["ms"] else 0.0, "peak_gbs": hbm_peak,
+                    "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
+            "per_kernel": {k: {"ms": v["ms"], "launches": v["launches"],
+                               "gmodmul_per_s": (v["modmul"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] else 0.0,
+                               "share_of_device_time": v["ms"] / dev_ms if dev_ms else 0.0} for k, v in stats.items()},
+        }
+        h2d = B * (ELL * 96) + B * (2 * ELL * 96 + 4576)   # generate: pre ; validate: pre + post + proof
+        d2h = B * (ELL * 96 + 4576) + B * 8                # generate: post + proof ; validate: verdict + status
+        line = {
+            "metric": METRIC, "value": total_proofs / dev_max, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * wall_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u32 (12x32-bit Montgomery limbs, IMAD.WIDE)",
+            "data": "synthetic",
+            "config": {"workload": "whisk_n128_roundtrip", "shuffled_elements": ELL, "proofs_per_gpu_per_step": B,
+                       "parallelism": f"proof-parallel x{world}, no data-path collective",
+                       "l2": "flushed between steps (256 MiB write)",
+                       "value_definition": "proofs / sum of CUDA-event kernel time (host Fiat-Shamir excluded)",
+                       "device": info["name"], "sm_count": info["sm_count"]},
+            "e2e": {"value": total_proofs / wall_max, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h,
+                    "note": "C ABI with host buffers; stage descriptors/scalars (about 36 B per MSM term) are extra H2D"},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "clocks": sampler.summary(),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                from oracle.cbackend import build as build_oracle
+
+                build_oracle()
+                cores = os.cpu_count() or 1
+                workers = min(cores, 32)
+                n, dt = run_reference_sample(workers, 1)
+                line["cpu_baseline"] = {
+                    "value": n / dt, "unit": UNIT, "cores": workers, "kind": "port",
+                    "sample": f"{workers} processes x 1 Whisk n=128 round trip on the CPU oracle (C 6x64 Montgomery "
+                              f"port + Python orchestration), {dt:.1f} s wall incl. process start-up",
+                    "published_reference": "README.md:20,24 — Prove 150.2 ms + Verify 12.3 ms on a Ryzen 7 3800XT "
+                                           "(16 threads) = 6.2 proofs/s excl. ShufflePermuteCommit and decompression",
+                }
+            except Exception as e:  # the baseline is reported, never required for the GPU number
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="independent Whisk round trips per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_main(args)
+    else:
+        gpu_main(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -87,6 +87,7 @@ def load_library():
     lib.cdl_whisk_generate_shuffle_proof_batch.argtypes = [vp, vp, sz, vp, C.POINTER(vp), vp, vp, sz, i32p]
     lib.cdl_whisk_is_valid_shuffle_proof_batch.argtypes = [vp, vp, sz, vp, vp, vp, sz, C.POINTER(vp), i32p, i32p]
     lib.cdl_host_selftest.argtypes = [vp, vp, vp, vp]
+    lib.cdl_engine_stats.argtypes = [vp, vp, vp, vp, vp, C.c_int]
     lib.cdl_launch_count.argtypes = [vp]
     lib.cdl_launch_count.restype = u64
     no_status = ("cdl_destroy", "cdl_last_error", "cdl_abi_version", "cdl_rand_free", "cdl_crs_free", "cdl_crs_ell",
@@ -343,6 +344,17 @@ def _ctx_whisk_is_valid_batch(self, crs: CRS, pre: bytes, post: bytes, proofs: b
     return list(ok), list(status)
 
 
+def _ctx_engine_stats(self, reset: bool = False):
+    """Per kernel class (msm, elem, decompress, compress): launches, event ms, algorithmic modmul / bytes."""
+    n = (C.c_uint64 * 4)()
+    ms = (C.c_double * 4)()
+    mm = (C.c_double * 4)()
+    by = (C.c_double * 4)()
+    self._chk(self.lib.cdl_engine_stats(self.h, n, ms, mm, by, 1 if reset else 0))
+    names = ("msm_small", "elem_scalar_mul", "decompress", "compress")
+    return {names[i]: {"launches": int(n[i]), "ms": ms[i], "modmul": mm[i], "bytes": by[i]} for i in range(4)}
+
+
 def _ctx_launch_count(self) -> int:
     return int(self.lib.cdl_launch_count(self.h))
 
@@ -358,3 +370,4 @@ Context.whisk_is_valid_shuffle_proof = _ctx_whisk_is_valid
 Context.whisk_generate_shuffle_proof_batch = _ctx_whisk_generate_batch
 Context.whisk_is_valid_shuffle_proof_batch = _ctx_whisk_is_valid_batch
 Context.launch_count = _ctx_launch_count
+Context.engine_stats = _ctx_engine_stats

@@ -105,6 +105,20 @@ void cdl_engine_free_(void* engine) { delete static_cast<Engine*>(engine); }
 
 uint64_t cdl_launch_count(cdl_ctx* c) { return c && c->engine ? static_cast<Engine*>(c->engine)->launches : 0; }
 
+int32_t cdl_engine_stats(cdl_ctx* c, uint64_t* launches, double* ms, double* modmul, double* bytes, int reset) {
+  if (!c) return CDL_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(c->mu);
+  Engine* E = engine_of(c);
+  for (int i = 0; i < 4; i++) {
+    if (launches) launches[i] = E->stats.n[i];
+    if (ms) ms[i] = E->stats.ms[i];
+    if (modmul) modmul[i] = E->stats.modmul[i];
+    if (bytes) bytes[i] = E->stats.bytes[i];
+  }
+  if (reset) E->stats = Engine::Stats();
+  return CDL_OK;
+}
+
 int32_t cdl_host_selftest(uint8_t* out32, const cdl_fr* a, const cdl_fr* b, cdl_fr* fr_out) {
   if (!out32 || !a || !b || !fr_out) return CDL_ERR_INVALID_ARG;
   cdlh::Transcript t("test protocol");

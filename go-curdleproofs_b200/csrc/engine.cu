@@ -48,6 +48,34 @@ Engine::~Engine() {
   }
 }
 
+// modmul(N) = min_c [6 N W + 28 2^(c-1) W + 9 c (W-1) + 14 W], W = ceil(256/c)
+double Engine::msm_algorithmic_modmul(uint64_t N) {
+  if (N == 0) return 0;
+  double best = 1e300;
+  for (int c = 1; c <= 24; c++) {
+    double W = (double)((256 + c - 1) / c);
+    double v = 6.0 * N * W + 28.0 * (double)(1ull << (c - 1)) * W + 9.0 * c * (W - 1) + 14.0 * W;
+    if (v < best) best = v;
+  }
+  return best;
+}
+
+void Engine::tick() { cudaEventRecord(ctx_->ev0, ctx_->stream); }
+void Engine::tock(int cls, double modmul, double bytes) {
+  cudaEventRecord(ctx_->ev1, ctx_->stream);
+  pending_cls_ = cls;
+  stats.n[cls]++;
+  stats.modmul[cls] += modmul;
+  stats.bytes[cls] += bytes;
+  launches++;
+}
+void Engine::finish_timing() {
+  if (pending_cls_ < 0) return;
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, ctx_->ev0, ctx_->ev1) == cudaSuccess) stats.ms[pending_cls_] += ms;
+  pending_cls_ = -1;
+}
+
 int32_t Engine::reserve(Staging& s, size_t bytes) {
   if (bytes <= s.cap) return CDL_OK;
   cudaStreamSynchronize(ctx_->stream);
@@ -94,10 +122,12 @@ int32_t Engine::upload_jac(uint32_t dst, const void* host_jac, size_t count) {
   if (rc) return rc;
   memcpy(s_jac_.h, host_jac, count * sizeof(cdl::G1Jac));
   CDL_CUDA(ctx_, cudaMemcpyAsync(s_jac_.d, s_jac_.h, count * sizeof(cdl::G1Jac), cudaMemcpyHostToDevice, ctx_->stream));
+  tick();
   cdl::launch_jac_to_affine((const cdl::G1Jac*)s_jac_.d, d_pool_ + dst, (int)count, ctx_->stream);
-  launches++;
+  tock(3, 0, 240.0 * count);
   CDL_CUDA(ctx_, cudaGetLastError());
   CDL_CUDA(ctx_, cudaStreamSynchronize(ctx_->stream));
+  finish_timing();
   return CDL_OK;
 }
 
@@ -128,11 +158,13 @@ int32_t Engine::compress(const std::vector<uint32_t>& src, std::vector<uint8_t>&
   if ((rc = reserve(s_idx_, n * 4)) || (rc = reserve(s_out_, n * 48))) return rc;
   memcpy(s_idx_.h, src.data(), n * 4);
   CDL_CUDA(ctx_, cudaMemcpyAsync(s_idx_.d, s_idx_.h, n * 4, cudaMemcpyHostToDevice, ctx_->stream));
+  tick();
   cdl::launch_compress_idx(d_pool_, (const uint32_t*)s_idx_.d, (uint8_t*)s_out_.d, (int)n, ctx_->stream);
-  launches++;
+  tock(3, 3.0 * n, 148.0 * n);
   CDL_CUDA(ctx_, cudaGetLastError());
   CDL_CUDA(ctx_, cudaMemcpyAsync(s_out_.h, s_out_.d, n * 48, cudaMemcpyDeviceToHost, ctx_->stream));
   CDL_CUDA(ctx_, cudaStreamSynchronize(ctx_->stream));
+  finish_timing();
   memcpy(out48.data(), s_out_.h, n * 48);
   return CDL_OK;
 }
@@ -147,11 +179,14 @@ int32_t Engine::decompress(const uint8_t* enc48, const std::vector<uint32_t>& ds
   memcpy(s_enc_.h, enc48, n * 48);
   CDL_CUDA(ctx_, cudaMemcpyAsync(s_idx_.d, s_idx_.h, n * 4, cudaMemcpyHostToDevice, ctx_->stream));
   CDL_CUDA(ctx_, cudaMemcpyAsync(s_enc_.d, s_enc_.h, n * 48, cudaMemcpyHostToDevice, ctx_->stream));
+  tick();
   cdl::launch_decompress_idx((const uint8_t*)s_enc_.d, d_pool_, (const uint32_t*)s_idx_.d, (uint8_t*)s_st_.d, (int)n, ctx_->stream);
-  launches++;
+  // sqrt = one fixed 381-bit exponentiation (~480 modmul) + subgroup check [r]P (3193 by the §8d convention)
+  tock(2, (480.0 + 3193.0) * n, 148.0 * n);
   CDL_CUDA(ctx_, cudaGetLastError());
   CDL_CUDA(ctx_, cudaMemcpyAsync(s_st_.h, s_st_.d, n, cudaMemcpyDeviceToHost, ctx_->stream));
   CDL_CUDA(ctx_, cudaStreamSynchronize(ctx_->stream));
+  finish_timing();
   memcpy(status.data(), s_st_.h, n);
   return CDL_OK;
 }
@@ -174,12 +209,16 @@ int32_t Engine::run_msm(MsmStage& st) {
   CDL_CUDA(ctx_, cudaMemcpyAsync(s_idx_.d, s_idx_.h, nterm * 4, cudaMemcpyHostToDevice, ctx_->stream));
   CDL_CUDA(ctx_, cudaMemcpyAsync(s_sc_.d, s_sc_.h, nterm * 32, cudaMemcpyHostToDevice, ctx_->stream));
   CDL_CUDA(ctx_, cudaMemcpyAsync(s_task_.d, s_task_.h, nt * sizeof(MsmTask), cudaMemcpyHostToDevice, ctx_->stream));
+  double alg = 0;
+  for (auto& t : st.tasks) alg += msm_algorithmic_modmul(t.term_cnt);
+  tick();
   cdl::launch_msm_small(d_pool_, (const uint32_t*)s_idx_.d, (const cdl::Fr*)s_sc_.d, (const MsmTask*)s_task_.d, (int)nt,
                         max_terms, d_pool_, (uint8_t*)s_out_.d, ctx_->stream);
-  launches++;
+  tock(0, alg, 128.0 * nterm);
   CDL_CUDA(ctx_, cudaGetLastError());
   CDL_CUDA(ctx_, cudaMemcpyAsync(s_out_.h, s_out_.d, nt * 48, cudaMemcpyDeviceToHost, ctx_->stream));
   CDL_CUDA(ctx_, cudaStreamSynchronize(ctx_->stream));
+  finish_timing();
   memcpy(st.out48.data(), s_out_.h, nt * 48);
   return CDL_OK;
 }
@@ -193,10 +232,12 @@ int32_t Engine::run_elem(const std::vector<ElemOp>& ops, const std::vector<Fr>& 
   memcpy(s_sc_.h, sc.data(), sc.size() * 32);
   CDL_CUDA(ctx_, cudaMemcpyAsync(s_ops_.d, s_ops_.h, n * sizeof(ElemOp), cudaMemcpyHostToDevice, ctx_->stream));
   CDL_CUDA(ctx_, cudaMemcpyAsync(s_sc_.d, s_sc_.h, sc.size() * 32, cudaMemcpyHostToDevice, ctx_->stream));
+  tick();
   cdl::launch_elem_ops(d_pool_, (const ElemOp*)s_ops_.d, (const cdl::Fr*)s_sc_.d, (int)n, ctx_->stream);
-  launches++;
+  tock(1, 3193.0 * n, 288.0 * n);  // §8d: 3193 modmul per scalar multiplication; src + add + dst points
   CDL_CUDA(ctx_, cudaGetLastError());
   CDL_CUDA(ctx_, cudaStreamSynchronize(ctx_->stream));
+  finish_timing();
   return CDL_OK;
 }
 

@@ -129,8 +129,17 @@ class Engine {
 
   cdl_ctx* ctx() { return ctx_; }
   ThreadPool& threads() { return pool_; }
-  // instrumentation for bench.py: kernels launched / stage time since reset
+  // instrumentation for bench.py: per kernel class (0 msm, 1 elementwise, 2 decompress,
+  // 3 compress / normalise): launches, CUDA-event time on the launching stream,
+  // algorithmic modmul (SURVEY.md §8d conventions) and algorithmic bytes
   uint64_t launches = 0;
+  struct Stats {
+    uint64_t n[4] = {};
+    double ms[4] = {};
+    double modmul[4] = {};
+    double bytes[4] = {};
+  } stats;
+  static double msm_algorithmic_modmul(uint64_t terms);
 
  private:
   cdl_ctx* ctx_;
@@ -145,6 +154,10 @@ class Engine {
   };
   Staging s_idx_, s_sc_, s_task_, s_out_, s_ops_, s_enc_, s_st_, s_jac_;
   int32_t reserve(Staging& s, size_t bytes);
+  void tick();                                   // event before a kernel
+  void tock(int cls, double modmul, double bytes);  // event after; call finish_timing() after the sync
+  int pending_cls_ = -1;
+  void finish_timing();
 };
 
 // Whisk proof wire walker (whisk/types.go:39-72, curdleproof.go:320-387):

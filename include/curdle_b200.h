@@ -187,6 +187,12 @@ int32_t cdl_whisk_is_valid_shuffle_proof_batch(cdl_ctx* ctx, const cdl_crs* crs,
  * "test protocol" challenge computed by the library's transcript code;
  * fr_out receives (a*b + a - b)^-1 * a^5 computed by the host Fr code. */
 int32_t cdl_host_selftest(uint8_t* out32, const cdl_fr* a, const cdl_fr* b, cdl_fr* fr_out);
+/* Per kernel class statistics of the protocol-level calls since the last reset
+ * (class 0 small-MSM, 1 elementwise scalar-mul/fold, 2 decompress, 3 compress /
+ * normalise): launches, CUDA-event milliseconds on the launching stream,
+ * algorithmic modmul (SURVEY.md §8d conventions) and algorithmic bytes.
+ * Each output array has 4 entries. */
+int32_t cdl_engine_stats(cdl_ctx* ctx, uint64_t* launches, double* ms, double* modmul, double* bytes, int reset);
 /* Number of GPU kernels launched by protocol-level calls on this context so far. */
 uint64_t cdl_launch_count(cdl_ctx* ctx);
 
