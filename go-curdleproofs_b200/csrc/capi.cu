@@ -110,7 +110,12 @@ int32_t cdl_g1_msm_batch(cdl_ctx* c, const cdl_g1_affine* points, const cdl_fr* 
     k_iota<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(d_idx, (uint32_t)total);
   }
   CDL_CUDA(c, cudaMemcpyAsync(d_tasks, tasks.data(), k * sizeof(MsmTask), cudaMemcpyHostToDevice, c->stream));
-  launch_msm_small(d_pts, d_idx, d_sc, d_tasks, (int)k, max_terms, d_out, nullptr, c->stream);
+  void* d_win = nullptr;
+  if (size_t wb = msm_window_scratch_bytes((int)k)) {
+    d_win = c->buf(5, wb);
+    if (!d_win) return c->fail(CDL_ERR_CUDA, "device allocation failed");
+  }
+  launch_msm_small(d_pts, d_idx, d_sc, d_tasks, (int)k, max_terms, d_out, nullptr, d_win, c->stream);
   CDL_CUDA(c, cudaGetLastError());
   CDL_CUDA(c, cudaMemcpyAsync(out, d_out, k * sizeof(G1Affine), cudaMemcpyDeviceToHost, c->stream));
   CDL_CUDA(c, cudaStreamSynchronize(c->stream));

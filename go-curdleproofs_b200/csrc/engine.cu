@@ -42,6 +42,7 @@ Engine::Engine(cdl_ctx* ctx) : ctx_(ctx), pool_(std::max(1u, std::min(64u, std::
 Engine::~Engine() {
   cudaSetDevice(ctx_->device);
   if (d_pool_) cudaFree(d_pool_);
+  if (d_win_) cudaFree(d_win_);
   for (Staging* s : {&s_idx_, &s_sc_, &s_task_, &s_out_, &s_ops_, &s_enc_, &s_st_, &s_jac_}) {
     if (s->h) cudaFreeHost(s->h);
     if (s->d) cudaFree(s->d);
@@ -211,10 +212,23 @@ int32_t Engine::run_msm(MsmStage& st) {
   CDL_CUDA(ctx_, cudaMemcpyAsync(s_task_.d, s_task_.h, nt * sizeof(MsmTask), cudaMemcpyHostToDevice, ctx_->stream));
   double alg = 0;
   for (auto& t : st.tasks) alg += msm_algorithmic_modmul(t.term_cnt);
+  void* d_win = nullptr;
+  if (size_t wb = cdl::msm_window_scratch_bytes((int)nt)) {
+    if (wb > win_cap_) {
+      cudaStreamSynchronize(ctx_->stream);
+      if (d_win_) cudaFree(d_win_);
+      d_win_ = nullptr;
+      win_cap_ = 0;
+      if (cudaMalloc(&d_win_, wb + wb / 4) != cudaSuccess) return ctx_->fail(CDL_ERR_CUDA, "window scratch allocation failed");
+      win_cap_ = wb + wb / 4;
+    }
+    d_win = d_win_;
+  }
   tick();
-  cdl::launch_msm_small(d_pool_, (const uint32_t*)s_idx_.d, (const cdl::Fr*)s_sc_.d, (const MsmTask*)s_task_.d, (int)nt,
-                        max_terms, d_pool_, (uint8_t*)s_out_.d, ctx_->stream);
+  int nk = cdl::launch_msm_small(d_pool_, (const uint32_t*)s_idx_.d, (const cdl::Fr*)s_sc_.d, (const MsmTask*)s_task_.d,
+                                 (int)nt, max_terms, d_pool_, (uint8_t*)s_out_.d, d_win, ctx_->stream);
   tock(0, alg, 128.0 * nterm);
+  launches += nk - 1;
   CDL_CUDA(ctx_, cudaGetLastError());
   CDL_CUDA(ctx_, cudaMemcpyAsync(s_out_.h, s_out_.d, nt * 48, cudaMemcpyDeviceToHost, ctx_->stream));
   CDL_CUDA(ctx_, cudaStreamSynchronize(ctx_->stream));

@@ -146,6 +146,8 @@ class Engine {
   ThreadPool pool_;
   cdl::G1Affine* d_pool_ = nullptr;
   size_t pool_cap_ = 0;
+  void* d_win_ = nullptr;  // window sums of the two-kernel MSM path
+  size_t win_cap_ = 0;
   // pinned host staging + device scratch, grow-only
   struct Staging {
     void* h = nullptr;

@@ -70,18 +70,14 @@ __device__ __forceinline__ void xyzz_shfl_down(G1Xyzz& r, const G1Xyzz& p, int d
   for (int i = 0; i < 48; i++) d[i] = __shfl_down_sync(0xffffffffu, s[i], delta, width);
 }
 
-// points: pool of affine points; idx[t] selects the base of term t (bit 31:
-// negate).  scalars[t]: gnark Montgomery fr.Element.  out_aff[j] / out_c48[j]:
-// result of task j (either pointer may be null).
-__global__ void __launch_bounds__(kMsmThreads, 1)
-k_msm_small(const G1Affine* __restrict__ points, const uint32_t* __restrict__ idx,
-            const Fr* __restrict__ scalars, const MsmTask* __restrict__ tasks,
-            G1Affine* __restrict__ out_aff, uint8_t* __restrict__ out_c48) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  const MsmTask task = tasks[blockIdx.x];
+// Phases 1-3 for one CTA / one task: on return lane 0 of every 8-lane group
+// holds the window sum S_w (w = tid >> 3) in `acc`.  Uses T*36 bytes of smem.
+__device__ __forceinline__ void msm_bucket_phases(const G1Affine* __restrict__ points, const uint32_t* __restrict__ idx,
+                                                  const Fr* __restrict__ scalars, const MsmTask& task,
+                                                  uint8_t* smem_raw, G1Xyzz& acc) {
   const int T = (int)task.term_cnt;
   const int tid = threadIdx.x;
-  // layout: kp[T][8] words, then pidx[T] words, then the combine scratch
+  // layout: kp[T][8] words, then pidx[T] words
   uint32_t* kp = reinterpret_cast<uint32_t*>(smem_raw);
   uint32_t* pidx = kp + (size_t)T * 8;
 
@@ -100,7 +96,6 @@ k_msm_small(const G1Affine* __restrict__ points, const uint32_t* __restrict__ id
   // ---- phase 2: bucket accumulation
   const int w = tid >> 3;
   const int mybucket = (tid & 7) + 1;
-  G1Xyzz acc;
   xyzz_set_inf(acc);
   int t = 0;
   while (true) {
@@ -133,9 +128,25 @@ k_msm_small(const G1Affine* __restrict__ points, const uint32_t* __restrict__ id
     bool take = step < 3 ? ((tid & 7) + off < kMsmBuckets) : ((tid & 7) < off);
     if (take) xyzz_add(acc, acc, other);
   }
+}
+
+// Latency path (few MSMs in flight): one CTA does everything for its task.
+// points: pool of affine points; idx[t] selects the base of term t (bit 31:
+// negate).  scalars[t]: gnark Montgomery fr.Element.  out_aff[task.out_idx] /
+// out_c48[j]: result of task j (either pointer may be null).
+__global__ void __launch_bounds__(kMsmThreads, 1)
+k_msm_small(const G1Affine* __restrict__ points, const uint32_t* __restrict__ idx,
+            const Fr* __restrict__ scalars, const MsmTask* __restrict__ tasks,
+            G1Affine* __restrict__ out_aff, uint8_t* __restrict__ out_c48) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const MsmTask task = tasks[blockIdx.x];
+  const int tid = threadIdx.x;
+  const int w = tid >> 3;
+  G1Xyzz acc;
+  msm_bucket_phases(points, idx, scalars, task, smem_raw, acc);
 
   // ---- phase 4: combine windows (Jacobian: cheaper doublings)
-  __syncthreads();  // kp / pidx are dead from here on; reuse shared memory
+  __syncthreads();  // the recode staging is dead from here on; reuse shared memory
   G1Jac* win = reinterpret_cast<G1Jac*>(smem_raw);
   if ((tid & 7) == 0) {
     G1Jac j;
@@ -168,6 +179,46 @@ k_msm_small(const G1Affine* __restrict__ points, const uint32_t* __restrict__ id
   }
 }
 
+// Throughput path (many MSMs in flight), kernel 1 of 2: the parallel phases only;
+// window sums go to global memory as Jacobian points, win[w * ntasks + task].
+__global__ void __launch_bounds__(kMsmThreads, 1)
+k_msm_buckets(const G1Affine* __restrict__ points, const uint32_t* __restrict__ idx, const Fr* __restrict__ scalars,
+              const MsmTask* __restrict__ tasks, G1Jac* __restrict__ win, int ntasks) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const MsmTask task = tasks[blockIdx.x];
+  const int tid = threadIdx.x;
+  G1Xyzz acc;
+  msm_bucket_phases(points, idx, scalars, task, smem_raw, acc);
+  if ((tid & 7) == 0) {
+    G1Jac j;
+    xyzz_to_jac(j, acc);
+    win[(size_t)(tid >> 3) * ntasks + blockIdx.x] = j;
+  }
+}
+
+// Kernel 2 of 2: one thread per MSM walks its 64 window sums top-down (Horner:
+// 4 doublings + 1 addition per window), normalises and stores.  The doubling
+// chain is inherently serial per MSM; with thousands of MSMs in flight it runs
+// at full lane efficiency instead of idling 511 of a CTA's 512 threads.
+__global__ void __launch_bounds__(64)
+k_msm_combine(const G1Jac* __restrict__ win, const MsmTask* __restrict__ tasks, int ntasks,
+              G1Affine* __restrict__ out_aff, uint8_t* __restrict__ out_c48) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= ntasks) return;
+  G1Jac acc = win[(size_t)(kMsmWindows - 1) * ntasks + j];
+#pragma unroll 1
+  for (int w = kMsmWindows - 2; w >= 0; w--) {
+#pragma unroll 1
+    for (int i = 0; i < kMsmC; i++) jac_dbl(acc, acc);
+    G1Jac s = win[(size_t)w * ntasks + j];
+    jac_add(acc, acc, s);
+  }
+  G1Affine a;
+  jac_to_affine(a, acc);
+  if (out_aff) out_aff[tasks[j].out_idx] = a;
+  if (out_c48) g1_compress_dev(out_c48 + 48 * (size_t)j, a);
+}
+
 // shared memory bytes for the largest task of a launch
 static size_t msm_small_smem_bytes(size_t max_terms) {
   size_t a = max_terms * 36;                       // kp + pidx
@@ -176,13 +227,27 @@ static size_t msm_small_smem_bytes(size_t max_terms) {
 }
 
 cudaError_t msm_small_init() {
-  return cudaFuncSetAttribute(k_msm_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsmMaxSmem);
+  cudaError_t e = cudaFuncSetAttribute(k_msm_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsmMaxSmem);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_msm_buckets, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsmMaxSmem);
 }
 
-void launch_msm_small(const G1Affine* points, const uint32_t* idx, const Fr* scalars, const MsmTask* tasks,
-                      int ntasks, size_t max_terms, G1Affine* out_aff, uint8_t* out_c48, cudaStream_t st) {
+size_t msm_window_scratch_bytes(int ntasks) {
+  return ntasks >= kMsmSplitThreshold ? (size_t)ntasks * kMsmWindows * sizeof(G1Jac) : 0;
+}
+
+int launch_msm_small(const G1Affine* points, const uint32_t* idx, const Fr* scalars, const MsmTask* tasks,
+                     int ntasks, size_t max_terms, G1Affine* out_aff, uint8_t* out_c48, void* win_scratch,
+                     cudaStream_t st) {
+  if (ntasks >= kMsmSplitThreshold && win_scratch != nullptr) {
+    size_t smem = max_terms * 36;
+    k_msm_buckets<<<ntasks, kMsmThreads, smem, st>>>(points, idx, scalars, tasks, (G1Jac*)win_scratch, ntasks);
+    k_msm_combine<<<(ntasks + 63) / 64, 64, 0, st>>>((const G1Jac*)win_scratch, tasks, ntasks, out_aff, out_c48);
+    return 2;
+  }
   k_msm_small<<<ntasks, kMsmThreads, msm_small_smem_bytes(max_terms), st>>>(points, idx, scalars, tasks, out_aff,
                                                                              out_c48);
+  return 1;
 }
 
 }  // namespace cdl

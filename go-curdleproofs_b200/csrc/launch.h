@@ -37,7 +37,12 @@ void launch_decompress_idx(const uint8_t* in48, G1Affine* pool, const uint32_t* 
                            cudaStream_t s);
 // one CTA per task; out_aff / out_c48 may be null
 cudaError_t msm_small_init();
-void launch_msm_small(const G1Affine* points, const uint32_t* idx, const Fr* scalars, const MsmTask* tasks,
-                      int ntasks, size_t max_terms, G1Affine* out_aff, uint8_t* out_c48, cudaStream_t st);
+// With >= kMsmSplitThreshold tasks and a scratch buffer of msm_window_scratch_bytes(ntasks)
+// the throughput path (bucket kernel + combine kernel) is used; returns the number of kernels launched.
+constexpr int kMsmSplitThreshold = 96;
+size_t msm_window_scratch_bytes(int ntasks);
+int launch_msm_small(const G1Affine* points, const uint32_t* idx, const Fr* scalars, const MsmTask* tasks,
+                     int ntasks, size_t max_terms, G1Affine* out_aff, uint8_t* out_c48, void* win_scratch,
+                     cudaStream_t st);
 
 }  // namespace cdl

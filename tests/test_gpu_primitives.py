@@ -164,3 +164,28 @@ def test_int_peak_runs(ctx):
     for kind in (0, 1, 2):
         ops, ms = ctx.int_peak(kind, 200)
         assert ops > 0 and ms > 0
+
+
+def test_msm_batch_throughput_path(ctx, pts):
+    """>= 96 MSMs in one call take the two-kernel path (bucket kernel + per-MSM
+    Horner combine); results must match the oracle exactly, incl. empty /
+    degenerate tasks."""
+    import random
+    random.seed(11)
+    r = Rand(78)
+    sizes = [random.choice([0, 1, 2, 3, 7, 16, 33, 64]) for _ in range(130)]
+    offs = [0]
+    for s in sizes:
+        offs.append(offs[-1] + s)
+    ps = [pts[random.randrange(len(pts))] for _ in range(offs[-1])]
+    ks = r.get_frs(offs[-1])
+    # degenerate content: infinity bases, zero scalars, P and -P
+    for i in range(0, len(ps), 17):
+        ps[i] = None
+    for i in range(5, len(ks), 23):
+        ks[i] = 0
+    got = affs_dec(ctx.g1_msm_batch(affs_enc(ps), frs_enc(ks), offs))
+    from oracle.cbackend import CBackend
+    cb = CBackend(accelerate_keccak=False)
+    want = [cb.msm(ps[offs[i]:offs[i + 1]], ks[offs[i]:offs[i + 1]]) for i in range(len(sizes))]
+    assert got == want
