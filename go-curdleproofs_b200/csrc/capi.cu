@@ -97,7 +97,7 @@ int32_t cdl_g1_msm_batch(cdl_ctx* c, const cdl_g1_affine* points, const cdl_fr* 
     tasks[j].pad = 0;
     if (tasks[j].term_cnt > max_terms) max_terms = tasks[j].term_cnt;
   }
-  if (max_terms > kMsmMaxTerms) return c->fail(CDL_ERR_TOO_LARGE, "msm: %zu terms exceed the small-MSM limit %zu", max_terms, (size_t)kMsmMaxTerms);
+  if (max_terms > kMsmMaxTerms && (int)k < kMsmSplitThreshold) return c->fail(CDL_ERR_TOO_LARGE, "msm: %zu terms exceed the small-MSM limit %zu", max_terms, (size_t)kMsmMaxTerms);
   G1Affine* d_pts = (G1Affine*)c->buf(0, (total + 1) * sizeof(G1Affine));
   Fr* d_sc = (Fr*)c->buf(1, (total + 1) * sizeof(Fr));
   uint32_t* d_idx = (uint32_t*)c->buf(2, (total + 1) * sizeof(uint32_t));
@@ -110,12 +110,21 @@ int32_t cdl_g1_msm_batch(cdl_ctx* c, const cdl_g1_affine* points, const cdl_fr* 
     k_iota<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(d_idx, (uint32_t)total);
   }
   CDL_CUDA(c, cudaMemcpyAsync(d_tasks, tasks.data(), k * sizeof(MsmTask), cudaMemcpyHostToDevice, c->stream));
-  void* d_win = nullptr;
-  if (size_t wb = msm_window_scratch_bytes((int)k)) {
-    d_win = c->buf(5, wb);
-    if (!d_win) return c->fail(CDL_ERR_CUDA, "device allocation failed");
+  if ((int)k >= kMsmSplitThreshold) {
+    std::vector<MsmSub> subs;
+    std::vector<MsmTask2> tasks2;
+    msm_build_subs(tasks.data(), k, subs, tasks2);
+    MsmSub* d_subs = (MsmSub*)c->buf(5, subs.size() * sizeof(MsmSub));
+    MsmTask2* d_t2 = (MsmTask2*)c->buf(6, tasks2.size() * sizeof(MsmTask2));
+    void* d_scr = c->buf(7, msm_tp_scratch_bytes(total, subs.size()));
+    if (!d_subs || !d_t2 || !d_scr) return c->fail(CDL_ERR_CUDA, "device allocation failed");
+    CDL_CUDA(c, cudaMemcpyAsync(d_subs, subs.data(), subs.size() * sizeof(MsmSub), cudaMemcpyHostToDevice, c->stream));
+    CDL_CUDA(c, cudaMemcpyAsync(d_t2, tasks2.data(), tasks2.size() * sizeof(MsmTask2), cudaMemcpyHostToDevice, c->stream));
+    CDL_CUDA(c, cudaStreamSynchronize(c->stream));  // subs/tasks2 are pageable host vectors
+    launch_msm_tp(d_pts, d_idx, d_sc, (int)total, d_subs, (int)subs.size(), d_t2, (int)k, d_out, nullptr, d_scr, c->stream);
+  } else {
+    launch_msm_small(d_pts, d_idx, d_sc, d_tasks, (int)k, max_terms, d_out, nullptr, c->stream);
   }
-  launch_msm_small(d_pts, d_idx, d_sc, d_tasks, (int)k, max_terms, d_out, nullptr, d_win, c->stream);
   CDL_CUDA(c, cudaGetLastError());
   CDL_CUDA(c, cudaMemcpyAsync(out, d_out, k * sizeof(G1Affine), cudaMemcpyDeviceToHost, c->stream));
   CDL_CUDA(c, cudaStreamSynchronize(c->stream));

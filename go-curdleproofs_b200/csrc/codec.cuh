@@ -42,16 +42,6 @@ __device__ __forceinline__ void g1_compress_dev(uint8_t* out, const G1Affine& p)
   out[0] |= fp_lex_largest(p.y) ? (kFlagCompressed | kFlagLargest) : kFlagCompressed;
 }
 
-// [r]P == infinity, r the group order (255-bit, top nibble 7: fits recode_w4)
-__device__ __forceinline__ bool g1_in_subgroup_dev(const G1Affine& p) {
-  uint32_t rr[8];
-#pragma unroll
-  for (int i = 0; i < 8; i++) rr[i] = FR_MOD_D[i];
-  G1Jac t;
-  jac_scalar_mul(t, p, rr);
-  return jac_is_inf(t);
-}
-
 // G1Affine.SetBytes for one compressed encoding; returns 0 or a reason code
 __device__ __forceinline__ uint32_t g1_decompress_dev(G1Affine& p, const uint8_t* in) {
   uint32_t flags = in[0] & 0xe0u;
@@ -79,7 +69,7 @@ __device__ __forceinline__ uint32_t g1_decompress_dev(G1Affine& p, const uint8_t
   if (fp_lex_largest(y) != want_largest) FpM::neg(y, y);
   p.x = x;
   p.y = y;
-  if (!g1_in_subgroup_dev(p)) return 4;
+  if (!g1_in_subgroup_endo(p)) return 4;
   return 0;
 }
 

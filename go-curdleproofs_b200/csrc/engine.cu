@@ -43,7 +43,7 @@ Engine::~Engine() {
   cudaSetDevice(ctx_->device);
   if (d_pool_) cudaFree(d_pool_);
   if (d_win_) cudaFree(d_win_);
-  for (Staging* s : {&s_idx_, &s_sc_, &s_task_, &s_out_, &s_ops_, &s_enc_, &s_st_, &s_jac_}) {
+  for (Staging* s : {&s_idx_, &s_sc_, &s_task_, &s_out_, &s_ops_, &s_enc_, &s_st_, &s_jac_, &s_sub_, &s_t2_}) {
     if (s->h) cudaFreeHost(s->h);
     if (s->d) cudaFree(s->d);
   }
@@ -198,8 +198,6 @@ int32_t Engine::run_msm(MsmStage& st) {
   if (!nt) return CDL_OK;
   size_t max_terms = 0;
   for (auto& t : st.tasks) max_terms = std::max<size_t>(max_terms, t.term_cnt);
-  if (max_terms > cdl::kMsmMaxTerms)
-    return ctx_->fail(CDL_ERR_TOO_LARGE, "msm of %zu terms exceeds the small-MSM limit %zu", max_terms, (size_t)cdl::kMsmMaxTerms);
   int32_t rc;
   if ((rc = reserve(s_idx_, (nterm + 1) * 4)) || (rc = reserve(s_sc_, (nterm + 1) * 32)) ||
       (rc = reserve(s_task_, nt * sizeof(MsmTask))) || (rc = reserve(s_out_, nt * 48)))
@@ -212,23 +210,40 @@ int32_t Engine::run_msm(MsmStage& st) {
   CDL_CUDA(ctx_, cudaMemcpyAsync(s_task_.d, s_task_.h, nt * sizeof(MsmTask), cudaMemcpyHostToDevice, ctx_->stream));
   double alg = 0;
   for (auto& t : st.tasks) alg += msm_algorithmic_modmul(t.term_cnt);
-  void* d_win = nullptr;
-  if (size_t wb = cdl::msm_window_scratch_bytes((int)nt)) {
+  if ((int)nt >= cdl::kMsmSplitThreshold) {
+    // throughput path: recode + warp-per-chunk + per-task combine
+    std::vector<cdl::MsmSub> subs;
+    std::vector<cdl::MsmTask2> tasks2;
+    cdl::msm_build_subs(st.tasks.data(), nt, subs, tasks2);
+    if ((rc = reserve(s_sub_, subs.size() * sizeof(cdl::MsmSub))) || (rc = reserve(s_t2_, tasks2.size() * sizeof(cdl::MsmTask2))))
+      return rc;
+    size_t wb = cdl::msm_tp_scratch_bytes(nterm, subs.size());
     if (wb > win_cap_) {
       cudaStreamSynchronize(ctx_->stream);
       if (d_win_) cudaFree(d_win_);
       d_win_ = nullptr;
       win_cap_ = 0;
-      if (cudaMalloc(&d_win_, wb + wb / 4) != cudaSuccess) return ctx_->fail(CDL_ERR_CUDA, "window scratch allocation failed");
+      if (cudaMalloc(&d_win_, wb + wb / 4) != cudaSuccess) return ctx_->fail(CDL_ERR_CUDA, "MSM scratch allocation failed");
       win_cap_ = wb + wb / 4;
     }
-    d_win = d_win_;
+    memcpy(s_sub_.h, subs.data(), subs.size() * sizeof(cdl::MsmSub));
+    memcpy(s_t2_.h, tasks2.data(), tasks2.size() * sizeof(cdl::MsmTask2));
+    CDL_CUDA(ctx_, cudaMemcpyAsync(s_sub_.d, s_sub_.h, subs.size() * sizeof(cdl::MsmSub), cudaMemcpyHostToDevice, ctx_->stream));
+    CDL_CUDA(ctx_, cudaMemcpyAsync(s_t2_.d, s_t2_.h, tasks2.size() * sizeof(cdl::MsmTask2), cudaMemcpyHostToDevice, ctx_->stream));
+    tick();
+    cdl::launch_msm_tp(d_pool_, (const uint32_t*)s_idx_.d, (const cdl::Fr*)s_sc_.d, (int)nterm, (const cdl::MsmSub*)s_sub_.d,
+                       (int)subs.size(), (const cdl::MsmTask2*)s_t2_.d, (int)nt, d_pool_, (uint8_t*)s_out_.d, d_win_,
+                       ctx_->stream);
+    tock(0, alg, 128.0 * nterm);
+    launches += 2;
+  } else {
+    if (max_terms > cdl::kMsmMaxTerms)
+      return ctx_->fail(CDL_ERR_TOO_LARGE, "msm of %zu terms exceeds the small-MSM limit %zu", max_terms, (size_t)cdl::kMsmMaxTerms);
+    tick();
+    cdl::launch_msm_small(d_pool_, (const uint32_t*)s_idx_.d, (const cdl::Fr*)s_sc_.d, (const MsmTask*)s_task_.d, (int)nt,
+                          max_terms, d_pool_, (uint8_t*)s_out_.d, ctx_->stream);
+    tock(0, alg, 128.0 * nterm);
   }
-  tick();
-  int nk = cdl::launch_msm_small(d_pool_, (const uint32_t*)s_idx_.d, (const cdl::Fr*)s_sc_.d, (const MsmTask*)s_task_.d,
-                                 (int)nt, max_terms, d_pool_, (uint8_t*)s_out_.d, d_win, ctx_->stream);
-  tock(0, alg, 128.0 * nterm);
-  launches += nk - 1;
   CDL_CUDA(ctx_, cudaGetLastError());
   CDL_CUDA(ctx_, cudaMemcpyAsync(s_out_.h, s_out_.d, nt * 48, cudaMemcpyDeviceToHost, ctx_->stream));
   CDL_CUDA(ctx_, cudaStreamSynchronize(ctx_->stream));

@@ -14,6 +14,7 @@
 // samepermutationargument.go:62-67).
 #pragma once
 #include "fields.cuh"
+#include "glv.cuh"
 
 namespace cdl {
 
@@ -340,6 +341,79 @@ CDL_FN void jac_scalar_mul(G1Jac& r, const G1Affine& p, const uint32_t* k) {
       jac_add(r, r, t);
     }
   }
+}
+
+
+// r = k * p via GLV: k = s0*(s1*|k1| + k2*lambda), phi(p) = (beta*x, y) = lambda*p.
+// 32 signed 4-bit windows, 4 doublings + up to 2 additions per window; the phi
+// part reuses the window table with X scaled by beta.  Same uniform schedule for
+// every lane.  k canonical little-endian words, k < r.
+CDL_FN void jac_scalar_mul_glv(G1Jac& r, const G1Affine& p, const uint32_t* k) {
+  if (aff_is_inf(p)) { jac_set_inf(r); return; }
+  Glv g;
+  glv_decompose(g, k);
+  G1Jac tab[8];  // tab[i] = (i+1) p
+  jac_from_affine(tab[0], p);
+  jac_dbl(tab[1], tab[0]);
+#pragma unroll 1
+  for (int i = 2; i < 8; i++) jac_add_mixed(tab[i], tab[i - 1], p);
+  int8_t dg[2][32];
+  recode_w4_128(dg[0], g.k1);
+  recode_w4_128(dg[1], g.k2);
+  Fp beta;
+  fp_set_beta(beta);
+  jac_set_inf(r);
+#pragma unroll 1
+  for (int i = 31; i >= 0; i--) {
+    if (i != 31) {
+#pragma unroll 1
+      for (int j = 0; j < 4; j++) jac_dbl(r, r);
+    }
+#pragma unroll 1
+    for (int h = 0; h < 2; h++) {
+      int d = dg[h][i];
+      if (d != 0) {
+        int a = d < 0 ? -d : d;
+        G1Jac t = tab[a - 1];
+        if (h == 1) FpM::mul(t.x, t.x, beta);
+        bool neg = (d < 0) != (h == 0 ? g.neg1 : g.neg2);
+        if (neg) FpM::neg(t.y, t.y);
+        jac_add(r, r, t);
+      }
+    }
+  }
+}
+
+// r = e * p for a public 64-bit e (MSB-first double-and-add on a Jacobian base)
+CDL_FN void jac_mul_u64(G1Jac& r, const G1Jac& p, uint64_t e) {
+  jac_set_inf(r);
+  bool started = false;
+#pragma unroll 1
+  for (int i = 63; i >= 0; i--) {
+    if (started) jac_dbl(r, r);
+    if ((e >> i) & 1) {
+      if (started) jac_add(r, r, p); else { r = p; started = true; }
+    }
+  }
+}
+
+// Subgroup membership by the endomorphism: P is in G1 iff P + [z^2] phi(P) = 0
+// (z^2 * lambda + 1 = r).  This is gnark-crypto's own G1 IsInSubGroup test
+// (126 doublings + 11 additions instead of a 255-bit multiplication by r).
+CDL_FN bool g1_in_subgroup_endo(const G1Affine& p) {
+  if (aff_is_inf(p)) return true;
+  const uint64_t kZ = 0xd201000000010000ull;  // |z|
+  G1Jac q, t;
+  Fp beta;
+  fp_set_beta(beta);
+  FpM::mul(q.x, p.x, beta);
+  q.y = p.y;
+  FpM::set_one(q.z);
+  jac_mul_u64(t, q, kZ);
+  q = t;
+  jac_mul_u64(t, q, kZ);
+  jac_add_mixed(t, t, p);
+  return jac_is_inf(t);
 }
 
 }  // namespace cdl

@@ -20,7 +20,7 @@ k_scalar_mul(const G1Affine* __restrict__ P, const Fr* __restrict__ s, int strid
   FrM::from_mont(k, km);
   G1Affine p = P[i];
   G1Jac r;
-  jac_scalar_mul(r, p, k.v);
+  jac_scalar_mul_glv(r, p, k.v);
   if (L != nullptr) {
     G1Affine l = L[i];
     jac_add_mixed(r, r, l);
@@ -55,7 +55,7 @@ k_elem_ops(G1Affine* __restrict__ pool, const ElemOp* __restrict__ ops, const Fr
   FrM::from_mont(k, km);
   G1Affine p = pool[op.src];
   G1Jac r;
-  jac_scalar_mul(r, p, k.v);
+  jac_scalar_mul_glv(r, p, k.v);
   if (op.add != kNoPoint) {
     G1Affine l = pool[op.add];
     jac_add_mixed(r, r, l);

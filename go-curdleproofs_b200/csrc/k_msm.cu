@@ -179,46 +179,6 @@ k_msm_small(const G1Affine* __restrict__ points, const uint32_t* __restrict__ id
   }
 }
 
-// Throughput path (many MSMs in flight), kernel 1 of 2: the parallel phases only;
-// window sums go to global memory as Jacobian points, win[w * ntasks + task].
-__global__ void __launch_bounds__(kMsmThreads, 1)
-k_msm_buckets(const G1Affine* __restrict__ points, const uint32_t* __restrict__ idx, const Fr* __restrict__ scalars,
-              const MsmTask* __restrict__ tasks, G1Jac* __restrict__ win, int ntasks) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  const MsmTask task = tasks[blockIdx.x];
-  const int tid = threadIdx.x;
-  G1Xyzz acc;
-  msm_bucket_phases(points, idx, scalars, task, smem_raw, acc);
-  if ((tid & 7) == 0) {
-    G1Jac j;
-    xyzz_to_jac(j, acc);
-    win[(size_t)(tid >> 3) * ntasks + blockIdx.x] = j;
-  }
-}
-
-// Kernel 2 of 2: one thread per MSM walks its 64 window sums top-down (Horner:
-// 4 doublings + 1 addition per window), normalises and stores.  The doubling
-// chain is inherently serial per MSM; with thousands of MSMs in flight it runs
-// at full lane efficiency instead of idling 511 of a CTA's 512 threads.
-__global__ void __launch_bounds__(64)
-k_msm_combine(const G1Jac* __restrict__ win, const MsmTask* __restrict__ tasks, int ntasks,
-              G1Affine* __restrict__ out_aff, uint8_t* __restrict__ out_c48) {
-  int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= ntasks) return;
-  G1Jac acc = win[(size_t)(kMsmWindows - 1) * ntasks + j];
-#pragma unroll 1
-  for (int w = kMsmWindows - 2; w >= 0; w--) {
-#pragma unroll 1
-    for (int i = 0; i < kMsmC; i++) jac_dbl(acc, acc);
-    G1Jac s = win[(size_t)w * ntasks + j];
-    jac_add(acc, acc, s);
-  }
-  G1Affine a;
-  jac_to_affine(a, acc);
-  if (out_aff) out_aff[tasks[j].out_idx] = a;
-  if (out_c48) g1_compress_dev(out_c48 + 48 * (size_t)j, a);
-}
-
 // shared memory bytes for the largest task of a launch
 static size_t msm_small_smem_bytes(size_t max_terms) {
   size_t a = max_terms * 36;                       // kp + pidx
@@ -227,27 +187,13 @@ static size_t msm_small_smem_bytes(size_t max_terms) {
 }
 
 cudaError_t msm_small_init() {
-  cudaError_t e = cudaFuncSetAttribute(k_msm_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsmMaxSmem);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(k_msm_buckets, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsmMaxSmem);
+  return cudaFuncSetAttribute(k_msm_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsmMaxSmem);
 }
 
-size_t msm_window_scratch_bytes(int ntasks) {
-  return ntasks >= kMsmSplitThreshold ? (size_t)ntasks * kMsmWindows * sizeof(G1Jac) : 0;
-}
-
-int launch_msm_small(const G1Affine* points, const uint32_t* idx, const Fr* scalars, const MsmTask* tasks,
-                     int ntasks, size_t max_terms, G1Affine* out_aff, uint8_t* out_c48, void* win_scratch,
-                     cudaStream_t st) {
-  if (ntasks >= kMsmSplitThreshold && win_scratch != nullptr) {
-    size_t smem = max_terms * 36;
-    k_msm_buckets<<<ntasks, kMsmThreads, smem, st>>>(points, idx, scalars, tasks, (G1Jac*)win_scratch, ntasks);
-    k_msm_combine<<<(ntasks + 63) / 64, 64, 0, st>>>((const G1Jac*)win_scratch, tasks, ntasks, out_aff, out_c48);
-    return 2;
-  }
+void launch_msm_small(const G1Affine* points, const uint32_t* idx, const Fr* scalars, const MsmTask* tasks,
+                      int ntasks, size_t max_terms, G1Affine* out_aff, uint8_t* out_c48, cudaStream_t st) {
   k_msm_small<<<ntasks, kMsmThreads, msm_small_smem_bytes(max_terms), st>>>(points, idx, scalars, tasks, out_aff,
                                                                              out_c48);
-  return 1;
 }
 
 }  // namespace cdl

@@ -37,12 +37,39 @@ void launch_decompress_idx(const uint8_t* in48, G1Affine* pool, const uint32_t* 
                            cudaStream_t s);
 // one CTA per task; out_aff / out_c48 may be null
 cudaError_t msm_small_init();
-// With >= kMsmSplitThreshold tasks and a scratch buffer of msm_window_scratch_bytes(ntasks)
-// the throughput path (bucket kernel + combine kernel) is used; returns the number of kernels launched.
+// --- throughput path (k_msm_tp.cu): tasks are cut into chunks ("subs") of at most
+// kMsmChunk terms; one warp per sub, one combine thread per task.
+struct MsmSub {
+  uint32_t term_off, term_cnt;
+};
+struct MsmTask2 {
+  uint32_t sub_off, sub_cnt, out_idx, pad;
+};
+constexpr uint32_t kMsmChunk = 256;
+size_t msm_tp_scratch_bytes(size_t nterm, size_t nsub);
+void launch_msm_tp(const G1Affine* points, const uint32_t* idx, const Fr* scalars, int nterm, const MsmSub* subs,
+                   int nsub, const MsmTask2* tasks, int ntasks, G1Affine* out_aff, uint8_t* out_c48, void* scratch,
+                   cudaStream_t st);
+// host helper: cut tasks into subs
+template <class VecSub, class VecTask2>
+inline void msm_build_subs(const MsmTask* tasks, size_t ntasks, VecSub& subs, VecTask2& tasks2) {
+  subs.clear();
+  tasks2.clear();
+  for (size_t j = 0; j < ntasks; j++) {
+    MsmTask2 t2{(uint32_t)subs.size(), 0, tasks[j].out_idx, 0};
+    for (uint32_t o = 0; o < tasks[j].term_cnt; o += kMsmChunk) {
+      uint32_t c = tasks[j].term_cnt - o < kMsmChunk ? tasks[j].term_cnt - o : kMsmChunk;
+      subs.push_back(MsmSub{tasks[j].term_off + o, c});
+      t2.sub_cnt++;
+    }
+    tasks2.push_back(t2);
+  }
+}
+
+// Latency path (k_msm.cu): one CTA per task.  Callers switch to the throughput path at
+// kMsmSplitThreshold tasks per launch.
 constexpr int kMsmSplitThreshold = 96;
-size_t msm_window_scratch_bytes(int ntasks);
-int launch_msm_small(const G1Affine* points, const uint32_t* idx, const Fr* scalars, const MsmTask* tasks,
-                     int ntasks, size_t max_terms, G1Affine* out_aff, uint8_t* out_c48, void* win_scratch,
-                     cudaStream_t st);
+void launch_msm_small(const G1Affine* points, const uint32_t* idx, const Fr* scalars, const MsmTask* tasks,
+                      int ntasks, size_t max_terms, G1Affine* out_aff, uint8_t* out_c48, cudaStream_t st);
 
 }  // namespace cdl

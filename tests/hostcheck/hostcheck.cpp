@@ -56,6 +56,29 @@ void hc_g1_scalar_mul(const G1Affine* p, const uint32_t* k, G1Affine* r, int n) 
   }
 }
 
+void hc_g1_scalar_mul_glv(const G1Affine* p, const uint32_t* k, G1Affine* r, int n) {
+  for (int i = 0; i < n; i++) {
+    G1Jac j;
+    jac_scalar_mul_glv(j, p[i], k + 8 * i);
+    jac_to_affine(r[i], j);
+  }
+}
+
+// k (8 words) -> |k1| (4 words), k2 (4 words), neg1, neg2
+void hc_glv_decompose(const uint32_t* k, uint32_t* k1, uint32_t* k2, int* neg1, int* neg2, int n) {
+  for (int i = 0; i < n; i++) {
+    Glv g;
+    glv_decompose(g, k + 8 * i);
+    for (int j = 0; j < 4; j++) { k1[4 * i + j] = g.k1[j]; k2[4 * i + j] = g.k2[j]; }
+    neg1[i] = g.neg1;
+    neg2[i] = g.neg2;
+  }
+}
+
+void hc_g1_in_subgroup(const G1Affine* p, int* out, int n) {
+  for (int i = 0; i < n; i++) out[i] = g1_in_subgroup_endo(p[i]);
+}
+
 int hc_on_curve(const G1Affine* p) { return aff_on_curve(*p); }
 
 }  // extern "C"

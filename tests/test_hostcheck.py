@@ -118,3 +118,57 @@ def test_scalar_mul(hc):
     hc.hc_g1_scalar_mul(b"".join(aff_enc(p) for p in ps), pack(ks, 32), out, len(ks))
     got = [aff_dec(out.raw[i * 96:(i + 1) * 96]) for i in range(len(ks))]
     assert got == [b.g1_mul(p, k) for p, k in zip(ps, ks)]
+
+
+def test_glv_decomposition_and_scalar_mul(hc):
+    random.seed(7)
+    lam = 0xAC45A4010001A40200000000FFFFFFFF
+    ks = [0, 1, 2, lam, lam - 1, lam + 1, (R - 1) // 2, (R + 1) // 2, R - 1, R - 2, lam * lam % R] + \
+         [random.randrange(R) for _ in range(300)]
+    n = len(ks)
+    k1 = (ctypes.c_uint32 * (4 * n))()
+    k2 = (ctypes.c_uint32 * (4 * n))()
+    n1 = (ctypes.c_int * n)()
+    n2 = (ctypes.c_int * n)()
+    hc.hc_glv_decompose(pack(ks, 32), k1, k2, n1, n2, n)
+    for i, k in enumerate(ks):
+        a = sum(k1[4 * i + j] << (32 * j) for j in range(4))
+        c = sum(k2[4 * i + j] << (32 * j) for j in range(4))
+        assert a < 2**127 and c < 2**127
+        val = ((-a if n1[i] else a) + (-c if n2[i] else c) * lam) % R
+        assert val == k, i
+    pts = [b.g1_mul(b.G1_GEN, random.randrange(R)) for _ in range(4)]
+    sel = ks[:11] + ks[11:31]
+    ps = [random.choice(pts) for _ in sel]
+    ps[4] = None
+    out = ctypes.create_string_buffer(96 * len(sel))
+    hc.hc_g1_scalar_mul_glv(b"".join(aff_enc(p) for p in ps), pack(sel, 32), out, len(sel))
+    got = [aff_dec(out.raw[i * 96:(i + 1) * 96]) for i in range(len(sel))]
+    assert got == [b.g1_mul(p, k) for p, k in zip(ps, sel)]
+
+
+def test_endomorphism_subgroup_check(hc):
+    random.seed(8)
+    z = 0xD201000000010000
+    h = (z + 1) ** 2 // 3
+    good = [b.g1_mul(b.G1_GEN, random.randrange(1, R)) for _ in range(3)] + [None]
+    bad = []
+    while len(bad) < 4:
+        x = random.randrange(P)
+        y = b.fp_sqrt((x**3 + 4) % P)
+        if y is None:
+            continue
+        Q = (x, y)
+        bad.append(Q)                                              # generic curve point
+        C = b._from_jac(b.g1_mul_jac_raw(Q, R))                    # cofactor-subgroup point
+        if C is not None:
+            bad.append(C)
+        S = b._from_jac(b.g1_mul_jac_raw(Q, R * (h // 3)))         # order-3 point
+        if S is not None:
+            bad.append(S)
+            bad.append(b.g1_add(good[0], S))                       # G1 point + small-order point
+    pts = good + bad
+    out = (ctypes.c_int * len(pts))()
+    hc.hc_g1_in_subgroup(b"".join(aff_enc(p) for p in pts), out, len(pts))
+    assert list(out) == [1] * len(good) + [0] * len(bad)
+    assert [int(b.g1_in_subgroup(p)) for p in pts] == list(out)
