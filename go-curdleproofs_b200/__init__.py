@@ -12,6 +12,9 @@ from .binding import (  # noqa: F401
     Context,
     CRS,
     Rand,
+    DeviceBuffer,
+    comm_unique_id,
+    comm_partition,
     G1_AFFINE_BYTES,
     G1_JAC_BYTES,
     FR_BYTES,

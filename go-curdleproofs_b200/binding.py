@@ -90,7 +90,22 @@ def load_library():
     lib.cdl_engine_stats.argtypes = [vp, vp, vp, vp, vp, C.c_int]
     lib.cdl_launch_count.argtypes = [vp]
     lib.cdl_launch_count.restype = u64
-    no_status = ("cdl_destroy", "cdl_last_error", "cdl_abi_version", "cdl_rand_free", "cdl_crs_free", "cdl_crs_ell",
+    f32p = C.POINTER(C.c_float)
+    lib.cdl_dev_alloc.argtypes = [vp, sz, C.POINTER(vp)]
+    lib.cdl_dev_free.argtypes = [vp, vp]
+    lib.cdl_dev_upload.argtypes = [vp, vp, vp, sz]
+    lib.cdl_dev_download.argtypes = [vp, vp, vp, sz]
+    lib.cdl_g1_scalar_mul_affine_device.argtypes = [vp, vp, vp, sz, sz, vp]
+    lib.cdl_g1_msm_device.argtypes = [vp, vp, vp, sz, C.c_uint32, C.c_uint32, i32, vp, f32p]
+    lib.cdl_set_msm_window.argtypes = [vp, i32]
+    lib.cdl_comm_unique_id.argtypes = [vp]
+    lib.cdl_comm_init.argtypes = [vp, vp, i32, i32]
+    lib.cdl_comm_destroy.argtypes = [vp]
+    lib.cdl_comm_partition.argtypes = [sz, i32, i32, i32, i32p, i32p, i32p, i32p]
+    lib.cdl_comm_partition.restype = None
+    lib.cdl_g1_msm_sharded_device.argtypes = [vp, vp, vp, sz, vp, f32p]
+    lib.cdl_g1_msm_sharded.argtypes = [vp, vp, vp, sz, vp]
+    no_status = ("cdl_comm_partition", "cdl_destroy", "cdl_last_error", "cdl_abi_version", "cdl_rand_free", "cdl_crs_free", "cdl_crs_ell",
                  "cdl_launch_count")
     for name in declared_symbols():
         fn = getattr(lib, name)  # AttributeError if the build lost a symbol
@@ -195,6 +210,109 @@ class Context:
         ops, ms = C.c_double(), C.c_double()
         self._chk(self.lib.cdl_int_peak(self.h, kind, iters, C.byref(ops), C.byref(ms)))
         return ops.value, ms.value
+
+
+class DeviceBuffer:
+    """Raw device memory owned by a Context (cdl_dev_alloc)."""
+
+    def __init__(self, ctx: "Context", nbytes: int):
+        self.ctx = ctx
+        self.nbytes = nbytes
+        p = C.c_void_p()
+        ctx._chk(ctx.lib.cdl_dev_alloc(ctx.h, nbytes, C.byref(p)))
+        self.ptr = p
+
+    def upload(self, data: bytes, offset: int = 0):
+        if offset + len(data) > self.nbytes:
+            raise ValueError("upload past the end of the device buffer")
+        self.ctx._chk(self.ctx.lib.cdl_dev_upload(self.ctx.h, C.c_void_p(self.ptr.value + offset), data, len(data)))
+
+    def download(self, nbytes: int | None = None, offset: int = 0) -> bytes:
+        nbytes = self.nbytes - offset if nbytes is None else nbytes
+        out = C.create_string_buffer(max(1, nbytes))
+        self.ctx._chk(self.ctx.lib.cdl_dev_download(self.ctx.h, out, C.c_void_p(self.ptr.value + offset), nbytes))
+        return out.raw[:nbytes]
+
+    def close(self):
+        if getattr(self, "ptr", None) and getattr(self.ctx, "h", None):
+            self.ctx.lib.cdl_dev_free(self.ctx.h, self.ptr)
+        self.ptr = None
+
+    __del__ = close
+
+
+def comm_unique_id() -> bytes:
+    """128-byte NCCL unique id (rank 0 creates it, the host application ships it to every rank)."""
+    lib = load_library()
+    out = C.create_string_buffer(128)
+    rc = lib.cdl_comm_unique_id(out)
+    if rc != 0:
+        raise CdlError(rc, "cdl_comm_unique_id (NCCL unavailable?)")
+    return out.raw
+
+
+def comm_partition(n: int, world: int, rank: int, window_bits: int = 0):
+    """Windows owned by `rank`: (first_window, window_step, n_windows, my_windows).  Pure host logic."""
+    lib = load_library()
+    a, b, c, d = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+    lib.cdl_comm_partition(n, world, rank, window_bits, C.byref(a), C.byref(b), C.byref(c), C.byref(d))
+    return a.value, b.value, c.value, d.value
+
+
+def _ctx_dev_buffer(self, nbytes: int) -> DeviceBuffer:
+    return DeviceBuffer(self, nbytes)
+
+
+def _ctx_g1_scalar_mul_affine_device(self, d_in: DeviceBuffer, d_s: DeviceBuffer, n: int, broadcast: bool,
+                                     d_out: DeviceBuffer):
+    self._chk(self.lib.cdl_g1_scalar_mul_affine_device(self.h, d_in.ptr, d_s.ptr, n, 0 if broadcast else 1, d_out.ptr))
+
+
+def _ctx_g1_msm_device(self, d_points, d_scalars, n: int, part_index: int = 0, part_count: int = 1,
+                       normalize: bool = True, d_out: DeviceBuffer | None = None):
+    """MultiExp on device vectors -> (G1Jac bytes, kernel ms).  d_points / d_scalars are DeviceBuffers or raw ints."""
+    own = d_out is None
+    if own:
+        d_out = DeviceBuffer(self, G1_JAC_BYTES)
+    ms = C.c_float()
+    pp = d_points.ptr if isinstance(d_points, DeviceBuffer) else C.c_void_p(int(d_points))
+    ps = d_scalars.ptr if isinstance(d_scalars, DeviceBuffer) else C.c_void_p(int(d_scalars))
+    self._chk(self.lib.cdl_g1_msm_device(self.h, pp, ps, n, part_index, part_count, 1 if normalize else 0, d_out.ptr,
+                                         C.byref(ms)))
+    res = d_out.download(G1_JAC_BYTES)
+    if own:
+        d_out.close()
+    return res, ms.value
+
+
+def _ctx_set_msm_window(self, bits: int):
+    self._chk(self.lib.cdl_set_msm_window(self.h, bits))
+
+
+def _ctx_comm_init(self, uid: bytes, rank: int, world: int):
+    self._chk(self.lib.cdl_comm_init(self.h, uid, rank, world))
+
+
+def _ctx_comm_destroy(self):
+    self._chk(self.lib.cdl_comm_destroy(self.h))
+
+
+def _ctx_g1_msm_sharded_device(self, d_points: DeviceBuffer, d_scalars: DeviceBuffer, n: int):
+    d_out = DeviceBuffer(self, G1_JAC_BYTES)
+    ms = C.c_float()
+    self._chk(self.lib.cdl_g1_msm_sharded_device(self.h, d_points.ptr, d_scalars.ptr, n, d_out.ptr, C.byref(ms)))
+    res = d_out.download(G1_JAC_BYTES)
+    d_out.close()
+    return res, ms.value
+
+
+def _ctx_g1_msm_sharded(self, points: bytes, scalars: bytes) -> bytes:
+    n = len(points) // G1_AFFINE_BYTES
+    if len(scalars) != n * FR_BYTES:
+        raise CdlError(-3, "len(points) != len(scalars)")
+    out = C.create_string_buffer(G1_JAC_BYTES)
+    self._chk(self.lib.cdl_g1_msm_sharded(self.h, points, scalars, n, out))
+    return out.raw
 
 
 class Rand:
@@ -359,6 +477,14 @@ def _ctx_launch_count(self) -> int:
     return int(self.lib.cdl_launch_count(self.h))
 
 
+Context.dev_buffer = _ctx_dev_buffer
+Context.g1_scalar_mul_affine_device = _ctx_g1_scalar_mul_affine_device
+Context.g1_msm_device = _ctx_g1_msm_device
+Context.set_msm_window = _ctx_set_msm_window
+Context.comm_init = _ctx_comm_init
+Context.comm_destroy = _ctx_comm_destroy
+Context.g1_msm_sharded_device = _ctx_g1_msm_sharded_device
+Context.g1_msm_sharded = _ctx_g1_msm_sharded
 Context.rand_get_g1_affines = _ctx_rand_get_g1_affines
 Context.generate_crs = _ctx_generate_crs
 Context.crs_from_points = _ctx_crs_from_points

@@ -52,15 +52,18 @@ int32_t cdl_create(int device, cdl_ctx** out) {
   cudaEventCreate(&c->ev1);
   // the small-MSM kernel stages up to ~6000 terms in shared memory
   msm_small_init();
+  if (const char* e = getenv("CDL_MSM_C")) c->msm_c_override = atoi(e);
   *out = c;
   return CDL_OK;
 }
 
 void cdl_engine_free_(void* engine);  // capi_protocol.cu
+int32_t cdl_big_msm_host_(cdl_ctx* c, const cdl_g1_affine* points, const cdl_fr* scalars, size_t n, cdl_g1_jac* out);  // capi_msm.cu
 
 void cdl_destroy(cdl_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  cdl_comm_destroy(c);
   if (c->engine) cdl_engine_free_(c->engine);
   c->free_all();
   cudaEventDestroy(c->ev0);
@@ -133,6 +136,11 @@ int32_t cdl_g1_msm_batch(cdl_ctx* c, const cdl_g1_affine* points, const cdl_fr* 
 
 int32_t cdl_g1_msm(cdl_ctx* c, const cdl_g1_affine* points, const cdl_fr* scalars, size_t n, cdl_g1_jac* out) {
   if (!c || !out || (n && (!points || !scalars))) return CDL_ERR_INVALID_ARG;
+  if (n > kBigMsmThreshold) {  // Pippenger path (k_msm_big.cu); the small-MSM kernels serve Prove/Verify sizes
+    std::lock_guard<std::mutex> lk(c->mu);
+    CDL_CUDA(c, cudaSetDevice(c->device));
+    return cdl_big_msm_host_(c, points, scalars, n, out);
+  }
   uint32_t offs[2] = {0, (uint32_t)n};
   cdl_g1_affine a;
   int32_t rc = cdl_g1_msm_batch(c, points, scalars, offs, 1, &a);
@@ -159,6 +167,16 @@ int32_t cdl_g1_sum_affine(cdl_ctx* c, const cdl_g1_affine* in, size_t n, cdl_g1_
   static const uint64_t fr_one[4] = {0x00000001fffffffeull, 0x5884b7fa00034802ull, 0x998c4fefecbc4ff5ull, 0x1824b159acc5056full};
   std::vector<cdl_fr> ones(n);
   for (size_t i = 0; i < n; i++) memcpy(ones[i].l, fr_one, 32);
+  if (n > kBigMsmThreshold) {
+    cdl_g1_jac j;
+    int32_t rc = cdl_g1_msm(c, in, ones.data(), n, &j);
+    if (rc != CDL_OK) return rc;
+    bool inf = true;
+    for (int i = 0; i < 6; i++) inf = inf && j.z.l[i] == 0;
+    if (inf) memset(out, 0, sizeof *out);
+    else { out->x = j.x; out->y = j.y; }  // normalised: Z = 1
+    return CDL_OK;
+  }
   uint32_t offs[2] = {0, (uint32_t)n};
   return cdl_g1_msm_batch(c, in, ones.data(), offs, 1, out);
 }

@@ -18,6 +18,10 @@ struct cdl_ctx {
   std::mutex mu;
   std::string err;
   void* engine = nullptr;  // cdlh::Engine, created on first protocol-level call
+  // multi-GPU communicator (capi_msm.cu): NCCL is dlopen'ed on first use
+  void* nccl_comm = nullptr;
+  int comm_rank = 0, comm_world = 1;
+  int msm_c_override = 0;  // CDL_MSM_C / cdl_set_msm_window: 0 = pick by size
   static constexpr int kSlots = 8;
   void* slot[kSlots] = {};
   size_t cap[kSlots] = {};

@@ -1,0 +1,486 @@
+// Large single MSM: signed-digit Pippenger with an on-GPU counting sort of bucket
+// indices.  Replaces (*G1Jac).MultiExp when one call carries thousands to
+// millions of terms (BASELINE.json config 5, the standalone sweep 2^10..2^22;
+// gnark's MultiExp is reached from msmaccumulator/msmaccumulator.go:59 and
+// common/util.go:75 with the same signature).
+//
+//   k_big_digits<0>  thread per scalar: Montgomery -> canonical, signed c-bit digits
+//                    d_w in [-2^(c-1), 2^(c-1)], histogram of (window, |d|) keys
+//   k_scan_*         exclusive prefix sum of the histogram (bucket offsets)
+//   k_big_digits<1>  same digits again, scatter (point index | sign) to the bucket's
+//                    slot — a counting sort; order inside a bucket is irrelevant
+//   k_big_accum      thread per bucket: XYZZ mixed additions of the bucket's points
+//   k_big_slice / k_big_large_finish
+//                    buckets above kBigLargeBucket entries (degenerate inputs: all
+//                    equal scalars, tiny scalars) are cut into slices summed by a
+//                    whole CTA each, so no thread ever walks a long list alone
+//   k_big_reduce1    thread per chunk of L buckets: running-sum trick inside the
+//                    chunk plus (chunk base)*sum by a short double-and-add
+//   k_big_sum        tree of plain sums down to one point per window
+//   k_big_horner     windows top-down (c doublings each), optional normalisation
+//
+// A rank of a multi-GPU job owns windows wfirst, wfirst + wstep, ... and returns
+// its partial sum already shifted, so the exchange is one all-gather of one point
+// per rank (k_big_combine adds them).
+#include "launch.h"
+
+namespace cdl {
+
+constexpr uint32_t kBigLargeBucket = 2048;  // entries; longer buckets take the slice path
+constexpr uint32_t kBigSliceLen = 2048;     // entries per slice (16 per thread of a 128-thread CTA)
+constexpr int kBigCtaThreads = 128;
+constexpr int kScanPerBlock = 1024;         // 256 threads x 4
+
+struct BigSliceRec {
+  uint32_t first, count;
+};
+struct BigLargeRec {
+  uint32_t bucket, slice_first, slice_count, pad;
+};
+
+// ---------------------------------------------------------------- digits
+// window w digit of canonical k (9 words, top word zero)
+__device__ __forceinline__ uint32_t big_raw_digit(const uint32_t* k9, int w, int c) {
+  int bit = w * c;
+  int word = bit >> 5, sh = bit & 31;
+  uint32_t lo = k9[word], hi = k9[word + 1];
+  uint32_t v = __funnelshift_r(lo, hi, sh);
+  return v & ((1u << c) - 1u);
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(256)
+k_big_digits(const Fr* __restrict__ scalars, int n, BigMsmDims dm, uint32_t* __restrict__ counters,
+             const uint32_t* __restrict__ offsets, uint32_t* __restrict__ entries) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < n;
+  uint32_t k9[10];
+#pragma unroll
+  for (int j = 0; j < 10; j++) k9[j] = 0;
+  if (live) {
+    Fr km = scalars[i], k;
+    FrM::from_mont(k, km);
+#pragma unroll
+    for (int j = 0; j < 8; j++) k9[j] = k.v[j];
+  }
+  const uint32_t lane = threadIdx.x & 31;
+  uint32_t carry = 0;
+  int next_local = dm.wfirst, j = 0;
+#pragma unroll 1
+  for (int w = 0; w < dm.W; w++) {
+    uint32_t t = (w * dm.c < 256 ? big_raw_digit(k9, w, dm.c) : 0u) + carry;
+    carry = t > (uint32_t)dm.M ? 1u : 0u;
+    if (w != next_local) continue;  // uniform: every lane walks the same windows
+    int32_t d = carry ? (int32_t)t - (int32_t)(2 * dm.M) : (int32_t)t;
+    uint32_t key = 0xffffffffu;
+    if (live && d != 0) key = (uint32_t)j * (uint32_t)dm.M + (uint32_t)(d < 0 ? -d : d) - 1u;
+    // warp-aggregated atomic: one add per distinct key in the warp (degenerate inputs put
+    // all 32 lanes on one counter)
+    uint32_t peers = __match_any_sync(0xffffffffu, key);
+    uint32_t leader = __ffs(peers) - 1;
+    uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+    uint32_t base = 0;
+    if (key != 0xffffffffu && lane == leader) base = atomicAdd(&counters[key], (uint32_t)__popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (PASS == 1 && key != 0xffffffffu)
+      entries[offsets[key] + base + rank] = (uint32_t)i | (d < 0 ? 0x80000000u : 0u);
+    next_local += dm.wstep;
+    j++;
+  }
+}
+
+// ---------------------------------------------------------------- scan (exclusive, nb + 1 outputs)
+__global__ void __launch_bounds__(256)
+k_scan_block_sums(const uint32_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ bsum) {
+  __shared__ uint32_t sh[256];
+  uint32_t base = blockIdx.x * kScanPerBlock + threadIdx.x * 4;
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) s += (base + k < n) ? in[base + k] : 0u;
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int st = 128; st >= 1; st >>= 1) {
+    if ((int)threadIdx.x < st) sh[threadIdx.x] += sh[threadIdx.x + st];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) bsum[blockIdx.x] = sh[0];
+}
+
+// single block: exclusive scan of nblk block sums in place (nblk <= 4096)
+__global__ void __launch_bounds__(1024)
+k_scan_top(uint32_t* __restrict__ bsum, uint32_t nblk) {
+  __shared__ uint32_t sh[1024];
+  uint32_t v[4];
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    uint32_t idx = threadIdx.x * 4 + k;
+    v[k] = idx < nblk ? bsum[idx] : 0u;
+    s += v[k];
+  }
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {  // Hillis-Steele inclusive scan
+    uint32_t t = (int)threadIdx.x >= off ? sh[threadIdx.x - off] : 0u;
+    __syncthreads();
+    sh[threadIdx.x] += t;
+    __syncthreads();
+  }
+  uint32_t run = sh[threadIdx.x] - s;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    uint32_t idx = threadIdx.x * 4 + k;
+    if (idx < nblk) bsum[idx] = run;
+    run += v[k];
+  }
+}
+
+// offsets[i] = exclusive prefix of counts; offsets[n] = total; counts are zeroed (they
+// become the scatter cursors)
+__global__ void __launch_bounds__(256)
+k_scan_apply(uint32_t* __restrict__ counts, uint32_t n, const uint32_t* __restrict__ bsum,
+             uint32_t* __restrict__ offsets) {
+  __shared__ uint32_t sh[256];
+  uint32_t base = blockIdx.x * kScanPerBlock + threadIdx.x * 4;
+  uint32_t v[4];
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    v[k] = (base + k < n) ? counts[base + k] : 0u;
+    s += v[k];
+  }
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int off = 1; off < 256; off <<= 1) {
+    uint32_t t = (int)threadIdx.x >= off ? sh[threadIdx.x - off] : 0u;
+    __syncthreads();
+    sh[threadIdx.x] += t;
+    __syncthreads();
+  }
+  uint32_t run = bsum[blockIdx.x] + sh[threadIdx.x] - s;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    if (base + k < n) {
+      offsets[base + k] = run;
+      counts[base + k] = 0;
+    }
+    run += v[k];
+    if (base + k + 1 == n) offsets[n] = run;
+  }
+}
+
+// ---------------------------------------------------------------- large buckets
+// meta[0] = number of large buckets, meta[1] = number of slices
+__global__ void __launch_bounds__(256)
+k_big_mark_large(const uint32_t* __restrict__ offsets, uint32_t nb, uint32_t* __restrict__ meta,
+                 BigLargeRec* __restrict__ large, BigSliceRec* __restrict__ slices) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  uint32_t s = offsets[b], cnt = offsets[b + 1] - s;
+  if (cnt <= kBigLargeBucket) return;
+  uint32_t ns = (cnt + kBigSliceLen - 1) / kBigSliceLen;
+  uint32_t li = atomicAdd(&meta[0], 1u);
+  uint32_t sf = atomicAdd(&meta[1], ns);
+  large[li] = BigLargeRec{b, sf, ns, 0};
+  for (uint32_t k = 0; k < ns; k++) {
+    uint32_t first = s + k * kBigSliceLen;
+    uint32_t c = cnt - k * kBigSliceLen;
+    slices[sf + k] = BigSliceRec{first, c < kBigSliceLen ? c : kBigSliceLen};
+  }
+}
+
+// CTA-wide sum of one XYZZ value per thread; result in sh[0]
+__device__ __forceinline__ void big_cta_tree(G1Xyzz* sh, const G1Xyzz& mine) {
+  const int t = threadIdx.x;
+  sh[t] = mine;
+  __syncthreads();
+#pragma unroll 1
+  for (int s = kBigCtaThreads / 2; s >= 1; s >>= 1) {
+    if (t < s) {
+      G1Xyzz a = sh[t], b = sh[t + s];
+      xyzz_add(a, a, b);
+      sh[t] = a;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(kBigCtaThreads)
+k_big_slice(const G1Affine* __restrict__ points, const uint32_t* __restrict__ entries,
+            const uint32_t* __restrict__ meta, const BigSliceRec* __restrict__ slices,
+            G1Xyzz* __restrict__ slice_out) {
+  __shared__ G1Xyzz sh[kBigCtaThreads];
+  const uint32_t nslices = meta[1];
+#pragma unroll 1
+  for (uint32_t s = blockIdx.x; s < nslices; s += gridDim.x) {
+    BigSliceRec r = slices[s];
+    G1Xyzz acc;
+    xyzz_set_inf(acc);
+#pragma unroll 1
+    for (uint32_t t = threadIdx.x; t < r.count; t += kBigCtaThreads) {
+      uint32_t en = entries[r.first + t];
+      G1Affine q = points[en & 0x7fffffffu];
+      if (en >> 31) FpM::neg(q.y, q.y);
+      xyzz_add_mixed(acc, acc, q);
+    }
+    big_cta_tree(sh, acc);
+    if (threadIdx.x == 0) slice_out[s] = sh[0];
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(kBigCtaThreads)
+k_big_large_finish(const uint32_t* __restrict__ meta, const BigLargeRec* __restrict__ large,
+                   const G1Xyzz* __restrict__ slice_out, G1Xyzz* __restrict__ buckets) {
+  __shared__ G1Xyzz sh[kBigCtaThreads];
+  const uint32_t nlarge = meta[0];
+#pragma unroll 1
+  for (uint32_t l = blockIdx.x; l < nlarge; l += gridDim.x) {
+    BigLargeRec r = large[l];
+    G1Xyzz acc;
+    xyzz_set_inf(acc);
+#pragma unroll 1
+    for (uint32_t t = threadIdx.x; t < r.slice_count; t += kBigCtaThreads) {
+      G1Xyzz p = slice_out[r.slice_first + t];
+      xyzz_add(acc, acc, p);
+    }
+    big_cta_tree(sh, acc);
+    if (threadIdx.x == 0) buckets[r.bucket] = sh[0];
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------- bucket accumulation
+__global__ void __launch_bounds__(128, 3)
+k_big_accum(const G1Affine* __restrict__ points, const uint32_t* __restrict__ entries,
+            const uint32_t* __restrict__ offsets, uint32_t nb, G1Xyzz* __restrict__ buckets) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  uint32_t s = offsets[b], e = offsets[b + 1];
+  G1Xyzz acc;
+  xyzz_set_inf(acc);
+  if (e - s <= kBigLargeBucket) {
+#pragma unroll 1
+    for (uint32_t t = s; t < e; t++) {
+      uint32_t en = entries[t];
+      G1Affine q = points[en & 0x7fffffffu];
+      if (en >> 31) FpM::neg(q.y, q.y);
+      xyzz_add_mixed(acc, acc, q);
+    }
+  }
+  buckets[b] = acc;  // large buckets are filled in by k_big_large_finish
+}
+
+// ---------------------------------------------------------------- bucket reduction
+// r = e * p, small public-size e (MSB-first double-and-add)
+__device__ __forceinline__ void xyzz_mul_small(G1Xyzz& r, const G1Xyzz& p, uint32_t e) {
+  xyzz_set_inf(r);
+  if (e == 0) return;
+  int top = 31 - __clz(e);
+  r = p;
+#pragma unroll 1
+  for (int i = top - 1; i >= 0; i--) {
+    xyzz_dbl(r, r);
+    if ((e >> i) & 1u) xyzz_add(r, r, p);
+  }
+}
+
+// thread (j, ch): P = sum_{i < L} (ch*L + i + 1) * B[j*M + ch*L + i]
+__global__ void __launch_bounds__(128, 3)
+k_big_reduce1(const G1Xyzz* __restrict__ buckets, int M, int L, int nchunks_total, G1Xyzz* __restrict__ out) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nchunks_total) return;
+  const int per = M / L;
+  const int j = t / per, ch = t - j * per;
+  const G1Xyzz* B = buckets + (size_t)j * M + (size_t)ch * L;
+  G1Xyzz run, acc;
+  xyzz_set_inf(run);
+  xyzz_set_inf(acc);
+#pragma unroll 1
+  for (int i = L - 1; i >= 0; i--) {
+    G1Xyzz b = B[i];
+    xyzz_add(run, run, b);
+    xyzz_add(acc, acc, run);
+  }
+  if (ch > 0) {
+    G1Xyzz s;
+    xyzz_mul_small(s, run, (uint32_t)ch * (uint32_t)L);
+    xyzz_add(acc, acc, s);
+  }
+  out[t] = acc;
+}
+
+// out[j*pout + g] = sum of in[j*pin + g*G .. +G)
+__global__ void __launch_bounds__(128, 3)
+k_big_sum(const G1Xyzz* __restrict__ in, int pin, int G, int pout, int total_out, G1Xyzz* __restrict__ out) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total_out) return;
+  const int j = t / pout, g = t - j * pout;
+  int lo = g * G, hi = lo + G < pin ? lo + G : pin;
+  G1Xyzz acc;
+  xyzz_set_inf(acc);
+#pragma unroll 1
+  for (int i = lo; i < hi; i++) {
+    G1Xyzz p = in[(size_t)j * pin + i];
+    xyzz_add(acc, acc, p);
+  }
+  out[t] = acc;
+}
+
+// acc = sum_j 2^(c*(wfirst + j*wstep)) * S_j ; optional normalisation to (x, y, 1) / (1, 1, 0)
+__global__ void k_big_horner(const G1Xyzz* __restrict__ S, BigMsmDims dm, int normalize, G1Jac* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  G1Jac acc;
+  jac_set_inf(acc);
+#pragma unroll 1
+  for (int j = dm.nlocal - 1; j >= 0; j--) {
+    if (j != dm.nlocal - 1) {
+#pragma unroll 1
+      for (int k = 0; k < dm.c * dm.wstep; k++) jac_dbl(acc, acc);
+    }
+    G1Xyzz s = S[j];
+    G1Jac sj;
+    xyzz_to_jac(sj, s);
+    jac_add(acc, acc, sj);
+  }
+#pragma unroll 1
+  for (int k = 0; k < dm.c * dm.wfirst; k++) jac_dbl(acc, acc);
+  if (normalize) {
+    G1Affine a;
+    jac_to_affine(a, acc);
+    jac_from_affine(acc, a);
+  }
+  out[0] = acc;
+}
+
+// out = sum of n Jacobian points (the per-rank partial sums), normalised
+__global__ void k_big_combine(const G1Jac* __restrict__ in, int n, G1Jac* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  G1Jac acc;
+  jac_set_inf(acc);
+#pragma unroll 1
+  for (int i = 0; i < n; i++) {
+    G1Jac p = in[i];
+    jac_add(acc, acc, p);
+  }
+  G1Affine a;
+  jac_to_affine(a, acc);
+  jac_from_affine(acc, a);
+  out[0] = acc;
+}
+
+// ---------------------------------------------------------------- host side
+int big_msm_pick_c(size_t n) {
+  int lg = 0;
+  while (((size_t)1 << (lg + 1)) <= n) lg++;
+  int c = lg <= 10 ? 8 : lg <= 12 ? 9 : lg <= 13 ? 10 : lg <= 14 ? 11 : lg <= 15 ? 12 : lg <= 17 ? 13
+          : lg <= 18 ? 14 : lg <= 19 ? 15 : 16;
+  return c;
+}
+
+BigMsmDims big_msm_dims(size_t n, int c, int wfirst, int wstep) {
+  BigMsmDims d;
+  d.n = (int)n;
+  d.c = c;
+  d.W = (256 + c - 1) / c;
+  d.M = 1 << (c - 1);
+  d.wfirst = wfirst;
+  d.wstep = wstep;
+  d.nlocal = wfirst < d.W ? (d.W - wfirst + wstep - 1) / wstep : 0;
+  d.nb = (uint32_t)d.nlocal * (uint32_t)d.M;
+  return d;
+}
+
+static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct BigLayout {
+  size_t counts, offsets, bsum, meta, entries, buckets, large, slices, slice_out, red0, red1, total;
+  uint32_t max_slices, max_large;
+};
+
+static BigLayout big_layout(const BigMsmDims& d) {
+  BigLayout L;
+  size_t nent = (size_t)d.n * (size_t)d.nlocal;
+  L.max_large = (uint32_t)(nent / kBigLargeBucket + 1);
+  L.max_slices = (uint32_t)(nent / kBigSliceLen + L.max_large + 1);
+  size_t o = 0;
+  L.counts = o; o += al256(((size_t)d.nb + 1) * 4);
+  L.offsets = o; o += al256(((size_t)d.nb + 2) * 4);
+  L.bsum = o; o += al256(4096 * 4);
+  L.meta = o; o += 256;
+  L.entries = o; o += al256((nent + 1) * 4);
+  L.buckets = o; o += al256(((size_t)d.nb + 1) * sizeof(G1Xyzz));
+  L.large = o; o += al256((size_t)L.max_large * sizeof(BigLargeRec));
+  L.slices = o; o += al256((size_t)L.max_slices * sizeof(BigSliceRec));
+  L.slice_out = o; o += al256((size_t)L.max_slices * sizeof(G1Xyzz));
+  size_t red = ((size_t)d.nb / 2 + (size_t)d.nlocal + 1) * sizeof(G1Xyzz);
+  L.red0 = o; o += al256(red);
+  L.red1 = o; o += al256(red);
+  L.total = o;
+  return L;
+}
+
+size_t big_msm_scratch_bytes(const BigMsmDims& d) { return big_layout(d).total; }
+
+// All launches go to `st`; nothing synchronises.  d_out receives one G1Jac.
+cudaError_t launch_big_msm(const G1Affine* points, const Fr* scalars, const BigMsmDims& d, int normalize,
+                           void* scratch, int sm_count, G1Jac* d_out, cudaStream_t st) {
+  uint8_t* base = (uint8_t*)scratch;
+  BigLayout L = big_layout(d);
+  uint32_t* counts = (uint32_t*)(base + L.counts);
+  uint32_t* offsets = (uint32_t*)(base + L.offsets);
+  uint32_t* bsum = (uint32_t*)(base + L.bsum);
+  uint32_t* meta = (uint32_t*)(base + L.meta);
+  uint32_t* entries = (uint32_t*)(base + L.entries);
+  G1Xyzz* buckets = (G1Xyzz*)(base + L.buckets);
+  BigLargeRec* large = (BigLargeRec*)(base + L.large);
+  BigSliceRec* slices = (BigSliceRec*)(base + L.slices);
+  G1Xyzz* slice_out = (G1Xyzz*)(base + L.slice_out);
+  G1Xyzz* red[2] = {(G1Xyzz*)(base + L.red0), (G1Xyzz*)(base + L.red1)};
+
+  if (d.nlocal == 0 || d.n == 0) {  // this rank owns no window: partial sum = infinity
+    G1Xyzz* one = red[0];
+    cudaMemsetAsync(one, 0, sizeof(G1Xyzz), st);  // zz = 0 => infinity
+    BigMsmDims e = d;
+    e.nlocal = 1; e.wfirst = 0; e.wstep = 1; e.c = 0;
+    k_big_horner<<<1, 32, 0, st>>>(one, e, normalize, d_out);
+    return cudaGetLastError();
+  }
+  const uint32_t nb = d.nb;
+  const uint32_t nblk = (nb + kScanPerBlock - 1) / kScanPerBlock;
+  if (nblk > 4096) return cudaErrorInvalidValue;
+  cudaMemsetAsync(counts, 0, ((size_t)nb + 1) * 4, st);
+  cudaMemsetAsync(meta, 0, 256, st);
+  const int gd = (d.n + 255) / 256;
+  k_big_digits<0><<<gd, 256, 0, st>>>(scalars, d.n, d, counts, nullptr, nullptr);
+  k_scan_block_sums<<<nblk, 256, 0, st>>>(counts, nb, bsum);
+  k_scan_top<<<1, 1024, 0, st>>>(bsum, nblk);
+  k_scan_apply<<<nblk, 256, 0, st>>>(counts, nb, bsum, offsets);
+  k_big_digits<1><<<gd, 256, 0, st>>>(scalars, d.n, d, counts, offsets, entries);
+  k_big_mark_large<<<(nb + 255) / 256, 256, 0, st>>>(offsets, nb, meta, large, slices);
+  k_big_accum<<<(nb + 127) / 128, 128, 0, st>>>(points, entries, offsets, nb, buckets);
+  k_big_slice<<<sm_count * 4, kBigCtaThreads, 0, st>>>(points, entries, meta, slices, slice_out);
+  k_big_large_finish<<<sm_count, kBigCtaThreads, 0, st>>>(meta, large, slice_out, buckets);
+  // bucket reduction
+  int Lc = d.M < 16 ? d.M : 16;
+  int per = d.M / Lc;
+  int total = d.nlocal * per;
+  k_big_reduce1<<<(total + 127) / 128, 128, 0, st>>>(buckets, d.M, Lc, total, red[0]);
+  int cur = 0;
+  while (per > 1) {
+    int G = per > 256 ? 16 : (per > 16 ? 8 : per);
+    int pout = (per + G - 1) / G;
+    int tot = d.nlocal * pout;
+    k_big_sum<<<(tot + 127) / 128, 128, 0, st>>>(red[cur], per, G, pout, tot, red[cur ^ 1]);
+    cur ^= 1;
+    per = pout;
+  }
+  k_big_horner<<<1, 32, 0, st>>>(red[cur], d, normalize, d_out);
+  return cudaGetLastError();
+}
+
+void launch_big_combine(const G1Jac* in, int n, G1Jac* out, cudaStream_t st) {
+  k_big_combine<<<1, 32, 0, st>>>(in, n, out);
+}
+
+}  // namespace cdl

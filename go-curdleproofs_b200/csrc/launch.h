@@ -72,4 +72,20 @@ constexpr int kMsmSplitThreshold = 96;
 void launch_msm_small(const G1Affine* points, const uint32_t* idx, const Fr* scalars, const MsmTask* tasks,
                       int ntasks, size_t max_terms, G1Affine* out_aff, uint8_t* out_c48, cudaStream_t st);
 
+
+// --- single large MSM (k_msm_big.cu): signed-digit Pippenger, counting sort of bucket
+// indices, thread-per-bucket accumulation.  A caller may own only the windows
+// wfirst, wfirst + wstep, ... (multi-GPU window partition).
+struct BigMsmDims {
+  int n, c, W, M, wfirst, wstep, nlocal;
+  uint32_t nb;  // nlocal * M buckets
+};
+constexpr size_t kBigMsmThreshold = 1024;  // cdl_g1_msm switches to the Pippenger path above this size
+int big_msm_pick_c(size_t n);
+BigMsmDims big_msm_dims(size_t n, int c, int wfirst, int wstep);
+size_t big_msm_scratch_bytes(const BigMsmDims& d);
+cudaError_t launch_big_msm(const G1Affine* points, const Fr* scalars, const BigMsmDims& d, int normalize,
+                           void* scratch, int sm_count, G1Jac* d_out, cudaStream_t st);
+void launch_big_combine(const G1Jac* in, int n, G1Jac* out, cudaStream_t st);
+
 }  // namespace cdl

@@ -196,6 +196,59 @@ int32_t cdl_engine_stats(cdl_ctx* ctx, uint64_t* launches, double* ms, double* m
 /* Number of GPU kernels launched by protocol-level calls on this context so far. */
 uint64_t cdl_launch_count(cdl_ctx* ctx);
 
+/* ---- large MSM, device-resident vectors, multi-GPU ----------------------
+ * cdl_g1_msm switches to a signed-digit Pippenger (on-GPU counting sort of
+ * bucket indices, thread-per-bucket XYZZ accumulation, chunked bucket
+ * reduction) above 1024 terms; the entry points below expose the same kernel
+ * chain on device-resident vectors and across the GPUs of one box
+ * (BASELINE.json config 5; gnark's MultiExp is what it replaces, e.g.
+ * msmaccumulator/msmaccumulator.go:59, common/util.go:75).                  */
+
+/* Raw device buffers on the context's GPU, for vectors that stay in HBM between
+ * calls (a CRS, the sweep's point vectors).  Plain cudaMalloc'ed memory: a host
+ * that already owns device memory (another CUDA library, a torch tensor) passes
+ * its own pointers to the *_device entry points instead. */
+int32_t cdl_dev_alloc(cdl_ctx* ctx, size_t bytes, void** d_ptr);
+int32_t cdl_dev_free(cdl_ctx* ctx, void* d_ptr);
+int32_t cdl_dev_upload(cdl_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
+int32_t cdl_dev_download(cdl_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
+
+/* (*G1Affine).ScalarMultiplication on device vectors (common/util.go:55-63), in place allowed. */
+int32_t cdl_g1_scalar_mul_affine_device(cdl_ctx* ctx, const cdl_g1_affine* d_in, const cdl_fr* d_s, size_t n,
+                                        size_t scalar_stride, cdl_g1_affine* d_out);
+
+/* (*G1Jac).MultiExp on device vectors.  part_index / part_count select the
+ * windows part_index, part_index + part_count, ... of the signed-digit
+ * decomposition (0 / 1 = the whole MSM); the partial sum is returned already
+ * shifted, so partial sums of all parts add up to the MSM.  normalize != 0
+ * returns (x, y, 1) or (1, 1, 0).  *kernel_ms (optional) receives the CUDA-event
+ * time of the kernel chain on the context's stream.  Synchronous. */
+int32_t cdl_g1_msm_device(cdl_ctx* ctx, const cdl_g1_affine* d_points, const cdl_fr* d_scalars, size_t n,
+                          uint32_t part_index, uint32_t part_count, int32_t normalize, cdl_g1_jac* d_out,
+                          float* kernel_ms);
+/* Override the Pippenger window width (2..18 bits; 0 = choose by size).  Tuning aid;
+ * the result does not depend on it.  Also settable as environment CDL_MSM_C. */
+int32_t cdl_set_msm_window(cdl_ctx* ctx, int32_t window_bits);
+
+/* One process per GPU: rank 0 calls cdl_comm_unique_id, the host application
+ * ships the 128 bytes to every rank (any transport), every rank calls
+ * cdl_comm_init (collective; NCCL over NVLink / NVSwitch, bound with dlopen). */
+int32_t cdl_comm_unique_id(uint8_t* id128);
+int32_t cdl_comm_init(cdl_ctx* ctx, const uint8_t* id128, int32_t rank, int32_t world);
+int32_t cdl_comm_destroy(cdl_ctx* ctx);
+/* Which windows rank `rank` of `world` owns for an MSM of n terms (window_bits 0 = choose by size). */
+void cdl_comm_partition(size_t n, int32_t world, int32_t rank, int32_t window_bits, int32_t* first_window,
+                        int32_t* window_step, int32_t* n_windows, int32_t* my_windows);
+/* Window-partitioned MSM: every rank passes the same (replicated) vectors, sums
+ * its own windows, the partial sums (one 144-byte point per rank) are
+ * all-gathered with NCCL and added on every rank; every rank receives the
+ * normalised result.  Collective over the communicator of cdl_comm_init
+ * (world == 1 needs no communicator). */
+int32_t cdl_g1_msm_sharded_device(cdl_ctx* ctx, const cdl_g1_affine* d_points, const cdl_fr* d_scalars, size_t n,
+                                  cdl_g1_jac* d_out, float* kernel_ms);
+int32_t cdl_g1_msm_sharded(cdl_ctx* ctx, const cdl_g1_affine* points, const cdl_fr* scalars, size_t n,
+                           cdl_g1_jac* out);
+
 /* ---- diagnostics / roofline ------------------------------------------- */
 /* out[i] = a[i] * b[i] in Fp (Montgomery).  K1 of SURVEY.md §7. */
 int32_t cdl_fp_mul(cdl_ctx* ctx, const cdl_fp* a, const cdl_fp* b, size_t n, cdl_fp* out);
