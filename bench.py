@@ -6,9 +6,10 @@ Workload (BASELINE.json configs[1]): Whisk shape, shuffled_elements = 124
 One *step* = one batch of B independent round trips (synthetic trackers),
 driven through the C ABI (cdl_whisk_*_batch) with HOST buffers.
 
-  value      proofs/s counting only device time: B*K / sum of the CUDA-event
-             durations of every kernel the step launched (inputs resident in
-             HBM; the host's Fiat-Shamir work between launches excluded)
+  value      proofs/s counting only device time: B*K / device busy time, the
+             union of the CUDA-event intervals of every kernel the step
+             launched on any lane's stream (inputs resident in HBM; the host's
+             Fiat-Shamir work between launches excluded)
   e2e.value  proofs/s wall clock through the C ABI, host<->device copies and the
              host-side transcript work inside the timed region
   roofline   the dominant kernel class against the integer-pipe peak
@@ -16,6 +17,11 @@ driven through the C ABI (cdl_whisk_*_batch) with HOST buffers.
              381-bit Montgomery product), HBM GB/s secondary
   cpu_baseline  the CPU oracle ("port": C 6x64 Montgomery restatement driven by
              the Python protocol restatement) on the host cores
+
+  msm        the standalone G1 MSM sweep (config 5) at a few sizes: device-
+             resident vectors, CUDA-event time of the Pippenger kernel chain;
+             at N > 1 GPUs the window-partitioned form (NCCL all-gather of
+             one partial sum per rank inside libcurdle_b200.so)
 
 `--impl reference` times that CPU path alone on all host cores.
 Multi-GPU: one process per GPU (torchrun), independent proofs sharded across
@@ -171,6 +177,65 @@ def make_trackers(ctx, pkg, ell: int, seeds):
     return out
 
 
+def msm_alg_modmul(n: int) -> int:
+    """min_c [6 n W + 28 2^(c-1) W + 9 c (W-1) + 14 W], W = ceil(256 / c)."""
+    best = None
+    for c in range(1, 25):
+        W = -(-256 // c)
+        v = 6 * n * W + 28 * (1 << (c - 1)) * W + 9 * c * (W - 1) + 14 * W
+        best = v if best is None or v < best else best
+    return best
+
+
+def msm_sweep(ctx, pkg, log2_sizes, reps, world, rank, peak_modmul, barrier):
+    """Config 5: points P_i = a_i*G (a_i = Rand(5).GetFr), scalars Rand(6).GetFr, both replicated on
+    every rank; the result is checked against (sum a_i*s_i)*G computed with host Fr arithmetic
+    through a 1-point scalar multiplication on the GPU."""
+    from oracle import bls12381 as b  # constants only
+    from util import R, RR_INV, aff_enc, fr_enc
+
+    nmax = 1 << max(log2_sizes)
+    r5, r6 = pkg.Rand(5), pkg.Rand(6)
+    dp, da, ds = ctx.dev_buffer(96 * nmax), ctx.dev_buffer(32 * nmax), ctx.dev_buffer(32 * nmax)
+    gen = aff_enc(b.G1_GEN)
+    chunk = 1 << min(16, min(log2_sizes))
+    acc = {lg: 0 for lg in log2_sizes}
+    done = 0
+    for o in range(0, nmax, chunk):
+        m = min(chunk, nmax - o)
+        A, S = r5.get_frs(m), r6.get_frs(m)
+        dp.upload(gen * m, 96 * o)
+        da.upload(A, 32 * o)
+        ds.upload(S, 32 * o)
+        part = 0
+        if rank == 0:  # host-side check value: sum a_i * s_i (Montgomery decode folded into one factor)
+            for i in range(m):
+                part += int.from_bytes(A[32 * i:32 * i + 32], "little") * int.from_bytes(S[32 * i:32 * i + 32], "little")
+        done += m
+        for lg in log2_sizes:
+            if done <= (1 << lg):
+                acc[lg] += part
+    ctx.g1_scalar_mul_affine_device(dp, da, nmax, False, dp)
+    out = []
+    for lg in log2_sizes:
+        n = 1 << lg
+        best, res = None, None
+        for _ in range(reps + 1):
+            barrier()
+            res, ms = ctx.g1_msm_sharded_device(dp, ds, n)
+            best = ms if best is None or ms < best else best
+        want_k = acc[lg] * RR_INV * RR_INV % R
+        want = ctx.g1_scalar_mul_affine(gen, fr_enc(want_k), broadcast=True)
+        ok = res[:96] == want and res[96:144] != bytes(48)
+        mm = msm_alg_modmul(n)
+        out.append({"log2n": lg, "ms": best, "mpoints_per_s": n / best / 1e3, "gmodmul_per_s": mm / best / 1e6,
+                    "frac_of_int_peak": mm / (best * 1e-3) / (peak_modmul * world), "check": "ok" if ok else "MISMATCH",
+                    "windows_per_rank": pkg.comm_partition(n, world, rank)[3]})
+    for d in (dp, da, ds):
+        d.close()
+    return out
+
+
 def gpu_main(args):
     import torch
     import torch.distributed as dist
@@ -184,6 +249,14 @@ def gpu_main(args):
     torch.cuda.set_device(local)
     pkg = importlib.import_module("go-curdleproofs_b200")
     ctx = pkg.Context(local)  # raises without a GPU / without the built library: no fallback
+    if args.lanes:
+        ctx.set_lanes(args.lanes)
+    if world > 1:  # the library's own NCCL communicator (window-partitioned MSM)
+        uid = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{local}")
+        if rank == 0:
+            uid = torch.tensor(list(pkg.comm_unique_id()), dtype=torch.uint8, device=f"cuda:{local}")
+        dist.broadcast(uid, 0)
+        ctx.comm_init(bytes(uid.cpu().tolist()), rank, world)
     info = ctx.device_info()
     B = args.batch
     crs = ctx.generate_crs(ELL, pkg.Rand(0))
@@ -233,8 +306,13 @@ def gpu_main(args):
     stats = ctx.engine_stats()
     launches = ctx.launch_count() - l0
     dev_ms = sum(v["ms"] for v in stats.values())
+    busy_ms = ctx.engine_busy_ms()
+    msm = None
+    if not args.no_msm:
+        msm = msm_sweep(ctx, pkg, [16, 20, 22] if not args.msm_sizes else [int(x) for x in args.msm_sizes.split(",")],
+                        2, world, rank, peak_modmul, barrier)
 
-    t = torch.tensor([wall, dev_ms / 1e3], dtype=torch.float64, device=f"cuda:{local}")
+    t = torch.tensor([wall, busy_ms / 1e3], dtype=torch.float64, device=f"cuda:{local}")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     wall_max, dev_max = float(t[0]), float(t[1])
@@ -274,7 +352,9 @@ def gpu_main(args):
             "config": {"workload": "whisk_n128_roundtrip", "shuffled_elements": ELL, "proofs_per_gpu_per_step": B,
                        "parallelism": f"proof-parallel x{world}, no data-path collective",
                        "l2": "flushed between steps (256 MiB write)",
-                       "value_definition": "proofs / sum of CUDA-event kernel time (host Fiat-Shamir excluded)",
+                       "value_definition": "proofs / device busy time = union of CUDA-event kernel intervals over all lanes "
+                                           "(host Fiat-Shamir excluded)",
+                       "lanes": args.lanes or 4,
                        "device": info["name"], "sm_count": info["sm_count"]},
             "e2e": {"value": total_proofs / wall_max, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h,
@@ -283,6 +363,10 @@ def gpu_main(args):
             "roofline": roofline,
             "clocks": sampler.summary(),
         }
+        if msm is not None:
+            line["msm"] = {"workload": "standalone G1 MSM, random points/scalars, device resident"
+                                       + (f", windows dealt to {world} ranks + NCCL all-gather" if world > 1 else ""),
+                           "sizes": msm}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 from oracle.cbackend import build as build_oracle
@@ -313,6 +397,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="independent Whisk round trips per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lanes", type=int, default=0, help="concurrent sub-batches per GPU (0 = library default)")
+    ap.add_argument("--no-msm", action="store_true", help="skip the standalone MSM sweep")
+    ap.add_argument("--msm-sizes", default="", help="comma separated log2 sizes for the MSM sweep")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_main(args)

@@ -65,6 +65,7 @@ def load_library():
     lib.cdl_g1_decompress.argtypes = [vp, vp, sz, vp, vp]
     lib.cdl_fp_mul.argtypes = [vp, vp, vp, sz, vp]
     lib.cdl_int_peak.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.cdl_int_peak_cfg.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     u64, i32p = C.c_uint64, C.POINTER(C.c_int32)
     lib.cdl_rand_new.argtypes = [u64, C.POINTER(vp)]
     lib.cdl_rand_free.argtypes = [vp]
@@ -88,6 +89,8 @@ def load_library():
     lib.cdl_whisk_is_valid_shuffle_proof_batch.argtypes = [vp, vp, sz, vp, vp, vp, sz, C.POINTER(vp), i32p, i32p]
     lib.cdl_host_selftest.argtypes = [vp, vp, vp, vp]
     lib.cdl_engine_stats.argtypes = [vp, vp, vp, vp, vp, C.c_int]
+    lib.cdl_engine_busy_ms.argtypes = [vp, C.POINTER(C.c_double)]
+    lib.cdl_set_lanes.argtypes = [vp, i32]
     lib.cdl_launch_count.argtypes = [vp]
     lib.cdl_launch_count.restype = u64
     f32p = C.POINTER(C.c_float)
@@ -210,6 +213,12 @@ class Context:
         ops, ms = C.c_double(), C.c_double()
         self._chk(self.lib.cdl_int_peak(self.h, kind, iters, C.byref(ops), C.byref(ms)))
         return ops.value, ms.value
+
+
+def _ctx_int_peak_cfg(self, kind: int, iters: int, blocks_per_sm: int, tpb: int):
+    ops, ms = C.c_double(), C.c_double()
+    self._chk(self.lib.cdl_int_peak_cfg(self.h, kind, iters, blocks_per_sm, tpb, C.byref(ops), C.byref(ms)))
+    return ops.value, ms.value
 
 
 class DeviceBuffer:
@@ -473,10 +482,21 @@ def _ctx_engine_stats(self, reset: bool = False):
     return {names[i]: {"launches": int(n[i]), "ms": ms[i], "modmul": mm[i], "bytes": by[i]} for i in range(4)}
 
 
+def _ctx_engine_busy_ms(self) -> float:
+    v = C.c_double()
+    self._chk(self.lib.cdl_engine_busy_ms(self.h, C.byref(v)))
+    return v.value
+
+
+def _ctx_set_lanes(self, lanes: int):
+    self._chk(self.lib.cdl_set_lanes(self.h, lanes))
+
+
 def _ctx_launch_count(self) -> int:
     return int(self.lib.cdl_launch_count(self.h))
 
 
+Context.int_peak_cfg = _ctx_int_peak_cfg
 Context.dev_buffer = _ctx_dev_buffer
 Context.g1_scalar_mul_affine_device = _ctx_g1_scalar_mul_affine_device
 Context.g1_msm_device = _ctx_g1_msm_device
@@ -496,4 +516,6 @@ Context.whisk_is_valid_shuffle_proof = _ctx_whisk_is_valid
 Context.whisk_generate_shuffle_proof_batch = _ctx_whisk_generate_batch
 Context.whisk_is_valid_shuffle_proof_batch = _ctx_whisk_is_valid_batch
 Context.launch_count = _ctx_launch_count
+Context.engine_busy_ms = _ctx_engine_busy_ms
+Context.set_lanes = _ctx_set_lanes
 Context.engine_stats = _ctx_engine_stats

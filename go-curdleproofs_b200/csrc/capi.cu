@@ -50,10 +50,40 @@ int32_t cdl_create(int device, cdl_ctx** out) {
   c->name = prop.name;
   cudaEventCreate(&c->ev0);
   cudaEventCreate(&c->ev1);
+  cudaEventCreate(&c->base_ev);
+  cudaEventRecord(c->base_ev, c->stream);
+  cudaStreamSynchronize(c->stream);
   // the small-MSM kernel stages up to ~6000 terms in shared memory
   msm_small_init();
   if (const char* e = getenv("CDL_MSM_C")) c->msm_c_override = atoi(e);
+  if (const char* e = getenv("CDL_LANES")) { int v = atoi(e); if (v >= 1 && v <= 16) c->n_lanes = v; }
   *out = c;
+  return CDL_OK;
+}
+
+// lane context `i` of a root context (created on first use; caller holds the root's mutex)
+cdl_ctx* cdl_lane_(cdl_ctx* root, size_t i) {
+  while (root->lanes.size() <= i) {
+    cdl_ctx* l = new cdl_ctx();
+    l->device = root->device;
+    l->sm_count = root->sm_count;
+    l->clock_khz = root->clock_khz;
+    l->name = root->name;
+    l->parent = root;
+    l->n_lanes = 1;
+    l->msm_c_override = root->msm_c_override;
+    if (cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking) != cudaSuccess) { delete l; return nullptr; }
+    cudaEventCreate(&l->ev0);
+    cudaEventCreate(&l->ev1);
+    root->lanes.push_back(l);
+  }
+  return root->lanes[i];
+}
+
+int32_t cdl_set_lanes(cdl_ctx* c, int32_t lanes) {
+  if (!c || lanes < 1 || lanes > 16) return CDL_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(c->mu);
+  c->n_lanes = lanes;
   return CDL_OK;
 }
 
@@ -64,10 +94,13 @@ void cdl_destroy(cdl_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cdl_comm_destroy(c);
+  for (cdl_ctx* l : c->lanes) cdl_destroy(l);
+  c->lanes.clear();
   if (c->engine) cdl_engine_free_(c->engine);
   c->free_all();
   cudaEventDestroy(c->ev0);
   cudaEventDestroy(c->ev1);
+  if (c->base_ev) cudaEventDestroy(c->base_ev);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -287,11 +320,16 @@ int32_t cdl_fp_mul(cdl_ctx* c, const cdl_fp* a, const cdl_fp* b, size_t n, cdl_f
 }
 
 int32_t cdl_int_peak(cdl_ctx* c, int kind, int iters, double* ops_per_s, double* ms_out) {
-  if (!c || iters <= 0 || kind < 0 || kind > 2) return CDL_ERR_INVALID_ARG;
+  return cdl_int_peak_cfg(c, kind, iters, kind >= 2 ? 2 : 8, 256, ops_per_s, ms_out);
+}
+
+int32_t cdl_int_peak_cfg(cdl_ctx* c, int kind, int iters, int blocks_per_sm, int tpb, double* ops_per_s,
+                         double* ms_out) {
+  if (!c || iters <= 0 || kind < 0 || kind > 4 || blocks_per_sm < 1 || blocks_per_sm > 32 || tpb < 32 || tpb > 1024)
+    return CDL_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> lk(c->mu);
   CDL_CUDA(c, cudaSetDevice(c->device));
-  const int tpb = 256;
-  const int blocks = c->sm_count * (kind == 2 ? 2 : 8);
+  const int blocks = c->sm_count * blocks_per_sm;
   void* d = c->buf(4, (size_t)blocks * tpb * sizeof(Fp));
   if (!d) return c->fail(CDL_ERR_CUDA, "device allocation failed");
   float best = 1e30f;
@@ -305,7 +343,7 @@ int32_t cdl_int_peak(cdl_ctx* c, int kind, int iters, double* ops_per_s, double*
     cudaEventElapsedTime(&ms, c->ev0, c->ev1);
     if (rep > 0 && ms < best) best = ms;
   }
-  double ops = (double)blocks * tpb * (double)iters * (kind == 2 ? 2.0 : 64.0);
+  double ops = (double)blocks * tpb * (double)iters * (kind == 2 ? 2.0 : kind == 3 ? 4.0 : kind == 4 ? 6.0 : 64.0);
   if (ops_per_s) *ops_per_s = ops / (best * 1e-3);
   if (ms_out) *ms_out = best;
   return CDL_OK;

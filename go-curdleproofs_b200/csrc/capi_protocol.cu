@@ -2,7 +2,10 @@
 // the Whisk wrappers (single and batched), on top of the batched engine.
 #include <cstring>
 #include <memory>
+#include <algorithm>
+#include <functional>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "host/engine.hpp"
@@ -12,6 +15,8 @@ using cdlh::Fr;
 using cdlh::Layout;
 
 static_assert(sizeof(Fr) == sizeof(cdl_fr), "host fr layout");
+
+extern "C" cdl_ctx* cdl_lane_(cdl_ctx* root, size_t i);  // capi.cu
 
 namespace {
 
@@ -88,7 +93,7 @@ struct Prep {
 
 // common prologue of the protocol calls
 int32_t begin_call(cdl_ctx* c, const cdl_crs* crs, size_t B, Engine** E, Layout* L) {
-  if (crs->ctx != c) return c->fail(CDL_ERR_INVALID_ARG, "crs belongs to another context");
+  if (crs->ctx != c->root()) return c->fail(CDL_ERR_INVALID_ARG, "crs belongs to another context");
   CDL_CUDA(c, cudaSetDevice(c->device));
   *E = engine_of(c);
   *L = Layout(crs->ell);
@@ -97,25 +102,93 @@ int32_t begin_call(cdl_ctx* c, const cdl_crs* crs, size_t B, Engine** E, Layout*
   return (*E)->load_crs(*L, crs);
 }
 
+constexpr size_t kMinLaneBatch = 32;  // below this a sub-batch no longer fills its launches
+
+// number of lanes a batch of B instances is cut into
+size_t lanes_for(cdl_ctx* c, size_t B) {
+  if (c->parent || c->n_lanes <= 1) return 1;
+  return std::max<size_t>(1, std::min<size_t>((size_t)c->n_lanes, B / kMinLaneBatch));
+}
+
+// runs fn(lane ctx, lo, hi) for contiguous sub-batches [lo, hi) concurrently, one host thread per lane
+int32_t run_lanes(cdl_ctx* c, size_t B, size_t G, const std::function<int32_t(cdl_ctx*, size_t, size_t)>& fn) {
+  std::lock_guard<std::mutex> lk(c->mu);
+  CDL_CUDA(c, cudaSetDevice(c->device));
+  std::vector<cdl_ctx*> lane(G);
+  for (size_t g = 0; g < G; g++)
+    if (!(lane[g] = cdl_lane_(c, g))) return c->fail(CDL_ERR_CUDA, "lane context creation failed");
+  std::vector<int32_t> rc(G, CDL_OK);
+  std::vector<std::thread> th;
+  for (size_t g = 0; g < G; g++) {
+    size_t lo = B * g / G, hi = B * (g + 1) / G;
+    th.emplace_back([&, g, lo, hi] { rc[g] = fn(lane[g], lo, hi); });
+  }
+  for (auto& t : th) t.join();
+  for (size_t g = 0; g < G; g++)
+    if (rc[g] != CDL_OK) return c->fail(rc[g], "%s", lane[g]->err.c_str());
+  return CDL_OK;
+}
+
+template <class F>
+void for_each_engine(cdl_ctx* c, F f) {
+  if (c->engine) f(static_cast<Engine*>(c->engine));
+  for (cdl_ctx* l : c->lanes)
+    if (l->engine) f(static_cast<Engine*>(l->engine));
+}
+
 }  // namespace
 
 extern "C" {
 
 void cdl_engine_free_(void* engine) { delete static_cast<Engine*>(engine); }
 
-uint64_t cdl_launch_count(cdl_ctx* c) { return c && c->engine ? static_cast<Engine*>(c->engine)->launches : 0; }
+uint64_t cdl_launch_count(cdl_ctx* c) {
+  if (!c) return 0;
+  std::lock_guard<std::mutex> lk(c->mu);
+  uint64_t n = 0;
+  for_each_engine(c, [&](Engine* E) { n += E->launches; });
+  return n;
+}
 
 int32_t cdl_engine_stats(cdl_ctx* c, uint64_t* launches, double* ms, double* modmul, double* bytes, int reset) {
   if (!c) return CDL_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> lk(c->mu);
-  Engine* E = engine_of(c);
   for (int i = 0; i < 4; i++) {
-    if (launches) launches[i] = E->stats.n[i];
-    if (ms) ms[i] = E->stats.ms[i];
-    if (modmul) modmul[i] = E->stats.modmul[i];
-    if (bytes) bytes[i] = E->stats.bytes[i];
+    if (launches) launches[i] = 0;
+    if (ms) ms[i] = 0;
+    if (modmul) modmul[i] = 0;
+    if (bytes) bytes[i] = 0;
   }
-  if (reset) E->stats = Engine::Stats();
+  for_each_engine(c, [&](Engine* E) {
+    for (int i = 0; i < 4; i++) {
+      if (launches) launches[i] += E->stats.n[i];
+      if (ms) ms[i] += E->stats.ms[i];
+      if (modmul) modmul[i] += E->stats.modmul[i];
+      if (bytes) bytes[i] += E->stats.bytes[i];
+    }
+    if (reset) { E->stats = Engine::Stats(); E->intervals.clear(); }
+  });
+  return CDL_OK;
+}
+
+int32_t cdl_engine_busy_ms(cdl_ctx* c, double* busy_ms) {
+  if (!c || !busy_ms) return CDL_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(c->mu);
+  std::vector<std::pair<float, float>> iv;
+  for_each_engine(c, [&](Engine* E) { iv.insert(iv.end(), E->intervals.begin(), E->intervals.end()); });
+  std::sort(iv.begin(), iv.end());
+  double busy = 0, cur_lo = 0, cur_hi = -1;
+  for (auto& p : iv) {
+    if (cur_hi < 0 || p.first > cur_hi) {
+      if (cur_hi >= 0) busy += cur_hi - cur_lo;
+      cur_lo = p.first;
+      cur_hi = p.second;
+    } else if (p.second > cur_hi) {
+      cur_hi = p.second;
+    }
+  }
+  if (cur_hi >= 0) busy += cur_hi - cur_lo;
+  *busy_ms = busy;
   return CDL_OK;
 }
 
@@ -381,6 +454,14 @@ int32_t cdl_whisk_generate_shuffle_proof_batch(cdl_ctx* c, const cdl_crs* crs, s
                                                size_t proof_cap, int32_t* status_out) {
   if (!c || !crs || !pre_trackers || !rands_in || !post_trackers || !proofs_out || !status_out || B == 0)
     return CDL_ERR_INVALID_ARG;
+  if (size_t G = lanes_for(c, B); G > 1) {
+    const size_t tb = (size_t)crs->ell * 96;
+    return run_lanes(c, B, G, [&](cdl_ctx* lane, size_t lo, size_t hi) {
+      return cdl_whisk_generate_shuffle_proof_batch(lane, crs, hi - lo, pre_trackers + lo * tb, rands_in + lo,
+                                                    post_trackers + lo * tb, proofs_out + lo * proof_cap, proof_cap,
+                                                    status_out + lo);
+    });
+  }
   std::lock_guard<std::mutex> lk(c->mu);
   Engine* E;
   Layout L(1);
@@ -453,6 +534,14 @@ int32_t cdl_whisk_is_valid_shuffle_proof_batch(cdl_ctx* c, const cdl_crs* crs, s
                                                cdl_rand* const* rands_in, int32_t* ok, int32_t* status_out) {
   if (!c || !crs || !pre_trackers || !post_trackers || !proofs || !rands_in || !ok || !status_out || B == 0)
     return CDL_ERR_INVALID_ARG;
+  if (size_t G = lanes_for(c, B); G > 1) {
+    const size_t tb = (size_t)crs->ell * 96;
+    return run_lanes(c, B, G, [&](cdl_ctx* lane, size_t lo, size_t hi) {
+      return cdl_whisk_is_valid_shuffle_proof_batch(lane, crs, hi - lo, pre_trackers + lo * tb, post_trackers + lo * tb,
+                                                    proofs + lo * proof_len, proof_len, rands_in + lo, ok + lo,
+                                                    status_out + lo);
+    });
+  }
   std::lock_guard<std::mutex> lk(c->mu);
   Engine* E;
   Layout L(1);

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "../../include/curdle_b200.h"
 
@@ -22,6 +23,15 @@ struct cdl_ctx {
   void* nccl_comm = nullptr;
   int comm_rank = 0, comm_world = 1;
   int msm_c_override = 0;  // CDL_MSM_C / cdl_set_msm_window: 0 = pick by size
+  // Batched protocol calls are cut into up to n_lanes sub-batches that advance
+  // concurrently, each on its own lane context (same device, own stream, engine,
+  // staging): one lane's host-side Fiat-Shamir work overlaps the other lanes'
+  // kernels, and their latency-bound kernels overlap each other.
+  cdl_ctx* parent = nullptr;
+  std::vector<cdl_ctx*> lanes;
+  int n_lanes = 4;               // CDL_LANES / cdl_set_lanes
+  cudaEvent_t base_ev = nullptr; // origin of the kernel-interval timeline (busy-time accounting)
+  cdl_ctx* root() { return parent ? parent : this; }
   static constexpr int kSlots = 8;
   void* slot[kSlots] = {};
   size_t cap[kSlots] = {};

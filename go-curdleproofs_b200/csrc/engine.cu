@@ -37,7 +37,11 @@ Layout::Layout(uint32_t ell_) {
 }
 
 // ------------------------------------------------------------------ plumbing
-Engine::Engine(cdl_ctx* ctx) : ctx_(ctx), pool_(std::max(1u, std::min(64u, std::thread::hardware_concurrency()))) {}
+// a lane engine shares the host cores with its sibling lanes
+Engine::Engine(cdl_ctx* ctx)
+    : ctx_(ctx),
+      pool_(ctx->parent ? std::max(2u, std::min(32u, std::thread::hardware_concurrency() / 2))
+                        : std::max(1u, std::min(64u, std::thread::hardware_concurrency()))) {}
 
 Engine::~Engine() {
   cudaSetDevice(ctx_->device);
@@ -74,6 +78,9 @@ void Engine::finish_timing() {
   if (pending_cls_ < 0) return;
   float ms = 0;
   if (cudaEventElapsedTime(&ms, ctx_->ev0, ctx_->ev1) == cudaSuccess) stats.ms[pending_cls_] += ms;
+  float t0 = 0;
+  if (cudaEventElapsedTime(&t0, ctx_->root()->base_ev, ctx_->ev0) == cudaSuccess && intervals.size() < (1u << 22))
+    intervals.emplace_back(t0, t0 + ms);
   pending_cls_ = -1;
 }
 

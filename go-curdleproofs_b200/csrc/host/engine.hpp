@@ -133,6 +133,9 @@ class Engine {
   // 3 compress / normalise): launches, CUDA-event time on the launching stream,
   // algorithmic modmul (SURVEY.md §8d conventions) and algorithmic bytes
   uint64_t launches = 0;
+  // [start, end) of every timed kernel chain on the root context's timeline (ms since base_ev);
+  // the union over all lanes is the device busy time
+  std::vector<std::pair<float, float>> intervals;
   struct Stats {
     uint64_t n[4] = {};
     double ms[4] = {};

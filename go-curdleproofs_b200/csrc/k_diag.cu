@@ -73,6 +73,57 @@ __global__ void k_peak_modmul(Fp* out, int iters, uint32_t seed) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = x;
 }
 
+// kind 3 / 4: two / three independent dependent-product chains per thread (ILP probe)
+__global__ void k_peak_modmul2(Fp* out, int iters, uint32_t seed) {
+  Fp x, y, u, v;
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    x.v[i] = FP_ONE_D[i] ^ (threadIdx.x * (i + 1) & 0xffff);
+    y.v[i] = FP_R2_D[i] ^ (seed & 0xff);
+    u.v[i] = FP_ONE_D[i] ^ (threadIdx.x * (i + 3) & 0xffff);
+    v.v[i] = FP_R2_D[i] ^ (seed & 0xf0);
+  }
+  x.v[11] &= 0x0fffffffu; y.v[11] &= 0x0fffffffu; u.v[11] &= 0x0fffffffu; v.v[11] &= 0x0fffffffu;
+  for (int i = 0; i < iters; i++) {
+    FpM::mul(x, x, y);
+    FpM::mul(u, u, v);
+    FpM::mul(y, y, x);
+    FpM::mul(v, v, u);
+  }
+  FpM::add(x, x, y);
+  FpM::add(u, u, v);
+  FpM::add(x, x, u);
+  out[blockIdx.x * blockDim.x + threadIdx.x] = x;
+}
+
+__global__ void k_peak_modmul3(Fp* out, int iters, uint32_t seed) {
+  Fp x, y, u, v, p, q;
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    x.v[i] = FP_ONE_D[i] ^ (threadIdx.x * (i + 1) & 0xffff);
+    y.v[i] = FP_R2_D[i] ^ (seed & 0xff);
+    u.v[i] = FP_ONE_D[i] ^ (threadIdx.x * (i + 3) & 0xffff);
+    v.v[i] = FP_R2_D[i] ^ (seed & 0xf0);
+    p.v[i] = FP_ONE_D[i] ^ (threadIdx.x * (i + 5) & 0xffff);
+    q.v[i] = FP_R2_D[i] ^ (seed & 0x0f);
+  }
+  x.v[11] &= 0x0fffffffu; y.v[11] &= 0x0fffffffu; u.v[11] &= 0x0fffffffu; v.v[11] &= 0x0fffffffu;
+  p.v[11] &= 0x0fffffffu; q.v[11] &= 0x0fffffffu;
+  for (int i = 0; i < iters; i++) {
+    FpM::mul(x, x, y);
+    FpM::mul(u, u, v);
+    FpM::mul(p, p, q);
+    FpM::mul(y, y, x);
+    FpM::mul(v, v, u);
+    FpM::mul(q, q, p);
+  }
+  FpM::add(x, x, y);
+  FpM::add(u, u, v);
+  FpM::add(p, p, q);
+  FpM::add(x, x, u);
+  FpM::add(x, x, p);
+  out[blockIdx.x * blockDim.x + threadIdx.x] = x;
+}
 
 void launch_fp_mul(const Fp* a, const Fp* b, Fp* out, int n, cudaStream_t s) {
   k_fp_mul<<<(n + 127) / 128, 128, 0, s>>>(a, b, out, n);
@@ -80,7 +131,9 @@ void launch_fp_mul(const Fp* a, const Fp* b, Fp* out, int n, cudaStream_t s) {
 void launch_peak(int kind, void* out, int blocks, int tpb, int iters, uint32_t seed, cudaStream_t s) {
   if (kind == 0) k_peak_imad<<<blocks, tpb, 0, s>>>((uint32_t*)out, iters, seed);
   else if (kind == 1) k_peak_imad_wide<<<blocks, tpb, 0, s>>>((uint64_t*)out, iters, seed);
-  else k_peak_modmul<<<blocks, tpb, 0, s>>>((Fp*)out, iters, seed);
+  else if (kind == 2) k_peak_modmul<<<blocks, tpb, 0, s>>>((Fp*)out, iters, seed);
+  else if (kind == 3) k_peak_modmul2<<<blocks, tpb, 0, s>>>((Fp*)out, iters, seed);
+  else k_peak_modmul3<<<blocks, tpb, 0, s>>>((Fp*)out, iters, seed);
 }
 
 }  // namespace cdl

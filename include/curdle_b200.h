@@ -193,6 +193,15 @@ int32_t cdl_host_selftest(uint8_t* out32, const cdl_fr* a, const cdl_fr* b, cdl_
  * algorithmic modmul (SURVEY.md §8d conventions) and algorithmic bytes.
  * Each output array has 4 entries. */
 int32_t cdl_engine_stats(cdl_ctx* ctx, uint64_t* launches, double* ms, double* modmul, double* bytes, int reset);
+/* Device busy time since the last cdl_engine_stats(.., reset = 1): the length of
+ * the union of all timed kernel intervals over every lane's stream (lanes overlap,
+ * so the per-class sums above can exceed it). */
+int32_t cdl_engine_busy_ms(cdl_ctx* ctx, double* busy_ms);
+/* A batched protocol call is cut into up to `lanes` sub-batches (default 4, at
+ * least 32 instances each) that advance concurrently on their own CUDA streams
+ * and host threads: one lane's host-side transcript work overlaps the other
+ * lanes' kernels.  Results do not depend on it.  Also environment CDL_LANES. */
+int32_t cdl_set_lanes(cdl_ctx* ctx, int32_t lanes);
 /* Number of GPU kernels launched by protocol-level calls on this context so far. */
 uint64_t cdl_launch_count(cdl_ctx* ctx);
 
@@ -257,6 +266,10 @@ int32_t cdl_fp_mul(cdl_ctx* ctx, const cdl_fp* a, const cdl_fp* b, size_t n, cdl
  * Montgomery products (practical modmul peak).  Writes the measured ops/s
  * (IMAD/s for 0-1, modmul/s for 2) and the kernel time. */
 int32_t cdl_int_peak(cdl_ctx* ctx, int kind, int iters, double* ops_per_s, double* ms);
+/* Same with an explicit launch shape (blocks per SM, threads per block) and two more
+ * kinds: 3 / 4 = two / three independent product chains per thread (ILP probes). */
+int32_t cdl_int_peak_cfg(cdl_ctx* ctx, int kind, int iters, int blocks_per_sm, int threads_per_block,
+                         double* ops_per_s, double* ms);
 
 #ifdef __cplusplus
 }
