@@ -149,10 +149,10 @@ int32_t cdl_g1_msm_batch(cdl_ctx* c, const cdl_g1_affine* points, const cdl_fr* 
   if ((int)k >= kMsmSplitThreshold) {
     std::vector<MsmSub> subs;
     std::vector<MsmTask2> tasks2;
-    msm_build_subs(tasks.data(), k, subs, tasks2);
+    msm_build_subs(tasks.data(), k, msm_tp_pick_chunk(total, c->sm_count), subs, tasks2);
     MsmSub* d_subs = (MsmSub*)c->buf(5, subs.size() * sizeof(MsmSub));
     MsmTask2* d_t2 = (MsmTask2*)c->buf(6, tasks2.size() * sizeof(MsmTask2));
-    void* d_scr = c->buf(7, msm_tp_scratch_bytes(total, subs.size()));
+    void* d_scr = c->buf(7, msm_tp_scratch_bytes(total, subs.size(), k));
     if (!d_subs || !d_t2 || !d_scr) return c->fail(CDL_ERR_CUDA, "device allocation failed");
     CDL_CUDA(c, cudaMemcpyAsync(d_subs, subs.data(), subs.size() * sizeof(MsmSub), cudaMemcpyHostToDevice, c->stream));
     CDL_CUDA(c, cudaMemcpyAsync(d_t2, tasks2.data(), tasks2.size() * sizeof(MsmTask2), cudaMemcpyHostToDevice, c->stream));

@@ -221,10 +221,10 @@ int32_t Engine::run_msm(MsmStage& st) {
     // throughput path: recode + warp-per-chunk + per-task combine
     std::vector<cdl::MsmSub> subs;
     std::vector<cdl::MsmTask2> tasks2;
-    cdl::msm_build_subs(st.tasks.data(), nt, subs, tasks2);
+    cdl::msm_build_subs(st.tasks.data(), nt, cdl::msm_tp_pick_chunk(nterm, ctx_->sm_count), subs, tasks2);
     if ((rc = reserve(s_sub_, subs.size() * sizeof(cdl::MsmSub))) || (rc = reserve(s_t2_, tasks2.size() * sizeof(cdl::MsmTask2))))
       return rc;
-    size_t wb = cdl::msm_tp_scratch_bytes(nterm, subs.size());
+    size_t wb = cdl::msm_tp_scratch_bytes(nterm, subs.size(), nt);
     if (wb > win_cap_) {
       cudaStreamSynchronize(ctx_->stream);
       if (d_win_) cudaFree(d_win_);
@@ -242,7 +242,7 @@ int32_t Engine::run_msm(MsmStage& st) {
                        (int)subs.size(), (const cdl::MsmTask2*)s_t2_.d, (int)nt, d_pool_, (uint8_t*)s_out_.d, d_win_,
                        ctx_->stream);
     tock(0, alg, 128.0 * nterm);
-    launches += 2;
+    launches += 3;
   } else {
     if (max_terms > cdl::kMsmMaxTerms)
       return ctx_->fail(CDL_ERR_TOO_LARGE, "msm of %zu terms exceeds the small-MSM limit %zu", max_terms, (size_t)cdl::kMsmMaxTerms);

@@ -29,7 +29,6 @@ namespace cdl {
 constexpr uint32_t kBigLargeBucket = 2048;  // entries; longer buckets take the slice path
 constexpr uint32_t kBigSliceLen = 2048;     // entries per slice (16 per thread of a 128-thread CTA)
 constexpr int kBigCtaThreads = 128;
-constexpr int kScanPerBlock = 1024;         // 256 threads x 4
 
 struct BigSliceRec {
   uint32_t first, count;
@@ -89,14 +88,17 @@ k_big_digits(const Fr* __restrict__ scalars, int n, BigMsmDims dm, uint32_t* __r
   }
 }
 
-// ---------------------------------------------------------------- scan (exclusive, nb + 1 outputs)
+// ---------------------------------------------------------------- scan (exclusive, n + 1 outputs)
+// Three launches: per-block sums, one block scanning the block sums, per-block rescan.
+// A block covers 256 * ipt counters (ipt <= 16), so n <= 4096 * 4096.
+constexpr int kScanMaxIpt = 16;
+
 __global__ void __launch_bounds__(256)
-k_scan_block_sums(const uint32_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ bsum) {
+k_scan_block_sums(const uint32_t* __restrict__ in, uint32_t n, int ipt, uint32_t* __restrict__ bsum) {
   __shared__ uint32_t sh[256];
-  uint32_t base = blockIdx.x * kScanPerBlock + threadIdx.x * 4;
+  uint32_t base = (blockIdx.x * 256u + threadIdx.x) * (uint32_t)ipt;
   uint32_t s = 0;
-#pragma unroll
-  for (int k = 0; k < 4; k++) s += (base + k < n) ? in[base + k] : 0u;
+  for (int k = 0; k < ipt; k++) s += (base + k < n) ? in[base + k] : 0u;
   sh[threadIdx.x] = s;
   __syncthreads();
   for (int st = 128; st >= 1; st >>= 1) {
@@ -138,15 +140,15 @@ k_scan_top(uint32_t* __restrict__ bsum, uint32_t nblk) {
 // offsets[i] = exclusive prefix of counts; offsets[n] = total; counts are zeroed (they
 // become the scatter cursors)
 __global__ void __launch_bounds__(256)
-k_scan_apply(uint32_t* __restrict__ counts, uint32_t n, const uint32_t* __restrict__ bsum,
+k_scan_apply(uint32_t* __restrict__ counts, uint32_t n, int ipt, const uint32_t* __restrict__ bsum,
              uint32_t* __restrict__ offsets) {
   __shared__ uint32_t sh[256];
-  uint32_t base = blockIdx.x * kScanPerBlock + threadIdx.x * 4;
-  uint32_t v[4];
+  uint32_t base = (blockIdx.x * 256u + threadIdx.x) * (uint32_t)ipt;
+  uint32_t v[kScanMaxIpt];
   uint32_t s = 0;
 #pragma unroll
-  for (int k = 0; k < 4; k++) {
-    v[k] = (base + k < n) ? counts[base + k] : 0u;
+  for (int k = 0; k < kScanMaxIpt; k++) {
+    v[k] = (k < ipt && base + k < n) ? counts[base + k] : 0u;
     s += v[k];
   }
   sh[threadIdx.x] = s;
@@ -159,14 +161,28 @@ k_scan_apply(uint32_t* __restrict__ counts, uint32_t n, const uint32_t* __restri
   }
   uint32_t run = bsum[blockIdx.x] + sh[threadIdx.x] - s;
 #pragma unroll
-  for (int k = 0; k < 4; k++) {
-    if (base + k < n) {
+  for (int k = 0; k < kScanMaxIpt; k++) {
+    if (k < ipt && base + k < n) {
       offsets[base + k] = run;
       counts[base + k] = 0;
+      if (base + k + 1 == n) offsets[n] = run + v[k];
     }
     run += v[k];
-    if (base + k + 1 == n) offsets[n] = run;
   }
+}
+
+// counts[0..n) -> offsets[0..n] (exclusive prefix, total in offsets[n]); counts zeroed; bsum: 4096 words
+cudaError_t launch_exclusive_scan(uint32_t* counts, uint32_t n, uint32_t* bsum, uint32_t* offsets, cudaStream_t st) {
+  if (n == 0) return cudaMemsetAsync(offsets, 0, 4, st);
+  int ipt = 4;
+  while ((uint64_t)4096 * 256 * ipt < n && ipt < kScanMaxIpt) ipt *= 2;
+  uint32_t per = 256u * (uint32_t)ipt;
+  uint32_t nblk = (n + per - 1) / per;
+  if (nblk > 4096) return cudaErrorInvalidValue;
+  k_scan_block_sums<<<nblk, 256, 0, st>>>(counts, n, ipt, bsum);
+  k_scan_top<<<1, 1024, 0, st>>>(bsum, nblk);
+  k_scan_apply<<<nblk, 256, 0, st>>>(counts, n, ipt, bsum, offsets);
+  return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------- large buckets
@@ -447,15 +463,12 @@ cudaError_t launch_big_msm(const G1Affine* points, const Fr* scalars, const BigM
     return cudaGetLastError();
   }
   const uint32_t nb = d.nb;
-  const uint32_t nblk = (nb + kScanPerBlock - 1) / kScanPerBlock;
-  if (nblk > 4096) return cudaErrorInvalidValue;
   cudaMemsetAsync(counts, 0, ((size_t)nb + 1) * 4, st);
   cudaMemsetAsync(meta, 0, 256, st);
   const int gd = (d.n + 255) / 256;
   k_big_digits<0><<<gd, 256, 0, st>>>(scalars, d.n, d, counts, nullptr, nullptr);
-  k_scan_block_sums<<<nblk, 256, 0, st>>>(counts, nb, bsum);
-  k_scan_top<<<1, 1024, 0, st>>>(bsum, nblk);
-  k_scan_apply<<<nblk, 256, 0, st>>>(counts, nb, bsum, offsets);
+  cudaError_t se = launch_exclusive_scan(counts, nb, bsum, offsets, st);
+  if (se != cudaSuccess) return se;
   k_big_digits<1><<<gd, 256, 0, st>>>(scalars, d.n, d, counts, offsets, entries);
   k_big_mark_large<<<(nb + 255) / 256, 256, 0, st>>>(offsets, nb, meta, large, slices);
   k_big_accum<<<(nb + 127) / 128, 128, 0, st>>>(points, entries, offsets, nb, buckets);

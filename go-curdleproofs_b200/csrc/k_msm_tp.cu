@@ -10,10 +10,13 @@
 //                 term (the term's point is one broadcast load), so lane efficiency is
 //                 ~15/16 regardless of the MSM size — unlike thread-per-bucket, whose
 //                 lanes idle on load imbalance when a window has few points per bucket.
-//   k_msm_combine thread per task : sums the chunk partials of each window and walks the
+//   k_msm_chunk_sum thread per (task, window): sums the chunk partials
+//   k_msm_combine thread per task : walks the
 //                 windows top-down (4 doublings + 1 addition), normalises, stores the affine
 //                 point and its 48-byte encoding.  The 124-doubling chain is serial per MSM
 //                 but runs at full lane efficiency across thousands of MSMs.
+#include <cstdlib>
+
 #include "codec.cuh"
 #include "launch.h"
 
@@ -100,8 +103,27 @@ k_msm_warp(const G1Affine* __restrict__ points, const MsmRec* __restrict__ rec, 
   win[(size_t)w * nsub + sub] = j;
 }
 
+// thread per (task, window): sum of the task's chunk partials, so that the serial Horner
+// chain of k_msm_combine_tp sees one point per window however finely a task was cut
+__global__ void __launch_bounds__(128)
+k_msm_chunk_sum(const G1Jac* __restrict__ win, const MsmTask2* __restrict__ tasks, int ntasks, int nsub,
+                G1Jac* __restrict__ wsum) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ntasks * kTpWindows) return;
+  const int w = t / ntasks, j = t - w * ntasks;
+  const MsmTask2 task = tasks[j];
+  G1Jac acc;
+  jac_set_inf(acc);
+#pragma unroll 1
+  for (uint32_t c = 0; c < task.sub_cnt; c++) {
+    G1Jac s = win[(size_t)w * nsub + task.sub_off + c];
+    jac_add(acc, acc, s);
+  }
+  wsum[(size_t)w * ntasks + j] = acc;
+}
+
 __global__ void __launch_bounds__(64)
-k_msm_combine_tp(const G1Jac* __restrict__ win, const MsmTask2* __restrict__ tasks, int ntasks, int nsub,
+k_msm_combine_tp(const G1Jac* __restrict__ wsum, const MsmTask2* __restrict__ tasks, int ntasks,
                  G1Affine* __restrict__ out_aff, uint8_t* __restrict__ out_c48) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= ntasks) return;
@@ -114,11 +136,8 @@ k_msm_combine_tp(const G1Jac* __restrict__ win, const MsmTask2* __restrict__ tas
 #pragma unroll 1
       for (int i = 0; i < 4; i++) jac_dbl(acc, acc);
     }
-#pragma unroll 1
-    for (uint32_t c = 0; c < task.sub_cnt; c++) {
-      G1Jac s = win[(size_t)w * nsub + task.sub_off + c];
-      jac_add(acc, acc, s);
-    }
+    G1Jac s = wsum[(size_t)w * ntasks + j];
+    jac_add(acc, acc, s);
   }
   G1Affine a;
   jac_to_affine(a, acc);
@@ -126,9 +145,26 @@ k_msm_combine_tp(const G1Jac* __restrict__ win, const MsmTask2* __restrict__ tas
   if (out_c48) g1_compress_dev(out_c48 + 48 * (size_t)j, a);
 }
 
-size_t msm_tp_scratch_bytes(size_t nterm, size_t nsub) {
+size_t msm_tp_scratch_bytes(size_t nterm, size_t nsub, size_t ntasks) {
   size_t rec = (nterm * sizeof(MsmRec) + 255) & ~(size_t)255;
-  return rec + nsub * kTpWindows * sizeof(G1Jac);
+  size_t win = (nsub * kTpWindows * sizeof(G1Jac) + 255) & ~(size_t)255;
+  return rec + win + ntasks * kTpWindows * sizeof(G1Jac);
+}
+
+// Chunk length for a launch.  Long chunks amortise the per-chunk bucket reduction (16 full
+// additions against 2 mixed additions per term); shorter ones give more warps and a shorter
+// tail.  Measured on B200 (batches of 256 - 2048 Whisk proofs): the reduction overhead of
+// 32 - 128-term chunks costs more than the tail they remove, so the longest chunk is the
+// default; CDL_MSM_CHUNK overrides it for experiments.
+uint32_t msm_tp_pick_chunk(size_t nterm, int sm_count) {
+  (void)nterm;
+  (void)sm_count;
+  static const uint32_t forced = [] {
+    const char* e = getenv("CDL_MSM_CHUNK");
+    int v = e ? atoi(e) : 0;
+    return (uint32_t)(v >= 8 && v <= 4096 ? v : 0);
+  }();
+  return forced ? forced : kMsmChunk;
 }
 
 void launch_msm_tp(const G1Affine* points, const uint32_t* idx, const Fr* scalars, int nterm, const MsmSub* subs,
@@ -136,10 +172,13 @@ void launch_msm_tp(const G1Affine* points, const uint32_t* idx, const Fr* scalar
                    cudaStream_t st) {
   MsmRec* rec = (MsmRec*)scratch;
   size_t rec_bytes = ((size_t)nterm * sizeof(MsmRec) + 255) & ~(size_t)255;
+  size_t win_bytes = ((size_t)nsub * kTpWindows * sizeof(G1Jac) + 255) & ~(size_t)255;
   G1Jac* win = (G1Jac*)((uint8_t*)scratch + rec_bytes);
+  G1Jac* wsum = (G1Jac*)((uint8_t*)scratch + rec_bytes + win_bytes);
   if (nterm > 0) k_msm_recode<<<(nterm + 127) / 128, 128, 0, st>>>(idx, scalars, rec, nterm);
   if (nsub > 0) k_msm_warp<<<(nsub + 3) / 4, 128, 0, st>>>(points, rec, subs, nsub, win);
-  k_msm_combine_tp<<<(ntasks + 63) / 64, 64, 0, st>>>(win, tasks, ntasks, nsub, out_aff, out_c48);
+  k_msm_chunk_sum<<<(ntasks * kTpWindows + 127) / 128, 128, 0, st>>>(win, tasks, ntasks, nsub, wsum);
+  k_msm_combine_tp<<<(ntasks + 63) / 64, 64, 0, st>>>(wsum, tasks, ntasks, out_aff, out_c48);
 }
 
 }  // namespace cdl

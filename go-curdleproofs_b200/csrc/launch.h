@@ -45,26 +45,30 @@ struct MsmSub {
 struct MsmTask2 {
   uint32_t sub_off, sub_cnt, out_idx, pad;
 };
-constexpr uint32_t kMsmChunk = 256;
-size_t msm_tp_scratch_bytes(size_t nterm, size_t nsub);
+constexpr uint32_t kMsmChunk = 256;  // longest chunk; msm_tp_pick_chunk shortens it for small launches
+size_t msm_tp_scratch_bytes(size_t nterm, size_t nsub, size_t ntasks);
+uint32_t msm_tp_pick_chunk(size_t nterm, int sm_count);
 void launch_msm_tp(const G1Affine* points, const uint32_t* idx, const Fr* scalars, int nterm, const MsmSub* subs,
                    int nsub, const MsmTask2* tasks, int ntasks, G1Affine* out_aff, uint8_t* out_c48, void* scratch,
                    cudaStream_t st);
 // host helper: cut tasks into subs
 template <class VecSub, class VecTask2>
-inline void msm_build_subs(const MsmTask* tasks, size_t ntasks, VecSub& subs, VecTask2& tasks2) {
+inline void msm_build_subs(const MsmTask* tasks, size_t ntasks, uint32_t chunk, VecSub& subs, VecTask2& tasks2) {
   subs.clear();
   tasks2.clear();
   for (size_t j = 0; j < ntasks; j++) {
     MsmTask2 t2{(uint32_t)subs.size(), 0, tasks[j].out_idx, 0};
-    for (uint32_t o = 0; o < tasks[j].term_cnt; o += kMsmChunk) {
-      uint32_t c = tasks[j].term_cnt - o < kMsmChunk ? tasks[j].term_cnt - o : kMsmChunk;
+    for (uint32_t o = 0; o < tasks[j].term_cnt; o += chunk) {
+      uint32_t c = tasks[j].term_cnt - o < chunk ? tasks[j].term_cnt - o : chunk;
       subs.push_back(MsmSub{tasks[j].term_off + o, c});
       t2.sub_cnt++;
     }
     tasks2.push_back(t2);
   }
 }
+
+// counts[0..n) -> offsets[0..n] exclusive prefix (total in offsets[n]); counts are zeroed; bsum: 4096 words
+cudaError_t launch_exclusive_scan(uint32_t* counts, uint32_t n, uint32_t* bsum, uint32_t* offsets, cudaStream_t st);
 
 // Latency path (k_msm.cu): one CTA per task.  Callers switch to the throughput path at
 // kMsmSplitThreshold tasks per launch.
