@@ -70,7 +70,7 @@ int pick_c(cdl_ctx* c, size_t n) {
 // partial (or whole) MSM on device buffers; result left in d_out (device), not synchronised
 int32_t big_msm_on_device(cdl_ctx* c, const G1Affine* d_pts, const Fr* d_sc, size_t n, uint32_t part, uint32_t parts,
                           int normalize, G1Jac* d_out) {
-  if (n >= ((size_t)1 << 31)) return c->fail(CDL_ERR_TOO_LARGE, "msm: %zu terms exceed 2^31 - 1", n);
+  if (n >= ((size_t)1 << 30)) return c->fail(CDL_ERR_TOO_LARGE, "msm: %zu terms exceed 2^30 - 1", n);
   BigMsmDims d = big_msm_dims(n, pick_c(c, n), (int)part, (int)parts);
   void* scr = c->buf(7, big_msm_scratch_bytes(d));
   if (!scr) return c->fail(CDL_ERR_CUDA, "msm scratch allocation of %zu bytes failed", big_msm_scratch_bytes(d));

@@ -4,11 +4,15 @@
 // gnark's MultiExp is reached from msmaccumulator/msmaccumulator.go:59 and
 // common/util.go:75 with the same signature).
 //
-//   k_big_digits<0>  thread per scalar: Montgomery -> canonical, signed c-bit digits
-//                    d_w in [-2^(c-1), 2^(c-1)], histogram of (window, |d|) keys
+//   k_big_phi        phi(P) = (beta*x, y) for every base (GLV endomorphism)
+//   k_big_digits<0>  thread per scalar: Montgomery -> canonical -> GLV halves (< 2^127),
+//                    signed c-bit digits d_w in [-2^(c-1), 2^(c-1)] of both halves,
+//                    histogram of (window, |d|) keys
 //   k_scan_*         exclusive prefix sum of the histogram (bucket offsets)
 //   k_big_digits<1>  same digits again, scatter (point index | sign) to the bucket's
 //                    slot — a counting sort; order inside a bucket is irrelevant
+//   k_big_size_sort  buckets ordered by decreasing length (counting sort), so that the
+//                    32 buckets of a warp have nearly equal trip counts
 //   k_big_accum      thread per bucket: XYZZ mixed additions of the bucket's points
 //   k_big_slice / k_big_large_finish
 //                    buckets above kBigLargeBucket entries (degenerate inputs: all
@@ -26,7 +30,7 @@
 
 namespace cdl {
 
-constexpr uint32_t kBigLargeBucket = 2048;  // entries; longer buckets take the slice path
+constexpr uint32_t kBigLargeBucket = 2048;  // upper bound of BigMsmDims::large (entries); longer buckets take the slice path
 constexpr uint32_t kBigSliceLen = 2048;     // entries per slice (16 per thread of a 128-thread CTA)
 constexpr int kBigCtaThreads = 128;
 
@@ -38,53 +42,81 @@ struct BigLargeRec {
 };
 
 // ---------------------------------------------------------------- digits
-// window w digit of canonical k (9 words, top word zero)
-__device__ __forceinline__ uint32_t big_raw_digit(const uint32_t* k9, int w, int c) {
+// Every scalar is split with the GLV endomorphism, k = +-|k1| +- k2*lambda with |k1|, k2 <
+// 2^127 (glv.cuh), so a term contributes to W = ceil(128/c) windows twice — once with P,
+// once with phi(P) = (beta*x, y), which k_big_phi tabulates — instead of to ceil(256/c)
+// windows once: the same number of bucket additions, but half the windows to reduce and
+// half the doublings in the final Horner chain.
+// window w digit of a 128-bit magnitude (6 words, top two zero)
+__device__ __forceinline__ uint32_t big_raw_digit(const uint32_t* k6, int w, int c) {
   int bit = w * c;
   int word = bit >> 5, sh = bit & 31;
-  uint32_t lo = k9[word], hi = k9[word + 1];
+  uint32_t lo = k6[word], hi = k6[word + 1];
   uint32_t v = __funnelshift_r(lo, hi, sh);
   return v & ((1u << c) - 1u);
 }
 
+__global__ void __launch_bounds__(256)
+k_big_phi(const G1Affine* __restrict__ points, int n, G1Affine* __restrict__ phi) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  G1Affine p = points[i];
+  Fp beta;
+  fp_set_beta(beta);
+  FpM::mul(p.x, p.x, beta);  // infinity (0, 0) stays (0, 0)
+  phi[i] = p;
+}
+
+// entry = index into [points | phi] (bit 31: negate)
 template <int PASS>
 __global__ void __launch_bounds__(256)
 k_big_digits(const Fr* __restrict__ scalars, int n, BigMsmDims dm, uint32_t* __restrict__ counters,
              const uint32_t* __restrict__ offsets, uint32_t* __restrict__ entries) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = i < n;
-  uint32_t k9[10];
+  uint32_t k6[2][6];
+  bool neg[2] = {false, false};
 #pragma unroll
-  for (int j = 0; j < 10; j++) k9[j] = 0;
+  for (int h = 0; h < 2; h++)
+#pragma unroll
+    for (int j = 0; j < 6; j++) k6[h][j] = 0;
   if (live) {
     Fr km = scalars[i], k;
     FrM::from_mont(k, km);
+    Glv g;
+    glv_decompose(g, k.v);
 #pragma unroll
-    for (int j = 0; j < 8; j++) k9[j] = k.v[j];
+    for (int j = 0; j < 4; j++) { k6[0][j] = g.k1[j]; k6[1][j] = g.k2[j]; }
+    neg[0] = g.neg1;
+    neg[1] = g.neg2;
   }
   const uint32_t lane = threadIdx.x & 31;
-  uint32_t carry = 0;
-  int next_local = dm.wfirst, j = 0;
 #pragma unroll 1
-  for (int w = 0; w < dm.W; w++) {
-    uint32_t t = (w * dm.c < 256 ? big_raw_digit(k9, w, dm.c) : 0u) + carry;
-    carry = t > (uint32_t)dm.M ? 1u : 0u;
-    if (w != next_local) continue;  // uniform: every lane walks the same windows
-    int32_t d = carry ? (int32_t)t - (int32_t)(2 * dm.M) : (int32_t)t;
-    uint32_t key = 0xffffffffu;
-    if (live && d != 0) key = (uint32_t)j * (uint32_t)dm.M + (uint32_t)(d < 0 ? -d : d) - 1u;
-    // warp-aggregated atomic: one add per distinct key in the warp (degenerate inputs put
-    // all 32 lanes on one counter)
-    uint32_t peers = __match_any_sync(0xffffffffu, key);
-    uint32_t leader = __ffs(peers) - 1;
-    uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-    uint32_t base = 0;
-    if (key != 0xffffffffu && lane == leader) base = atomicAdd(&counters[key], (uint32_t)__popc(peers));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (PASS == 1 && key != 0xffffffffu)
-      entries[offsets[key] + base + rank] = (uint32_t)i | (d < 0 ? 0x80000000u : 0u);
-    next_local += dm.wstep;
-    j++;
+  for (int h = 0; h < 2; h++) {
+    uint32_t carry = 0;
+    int next_local = dm.wfirst, j = 0;
+#pragma unroll 1
+    for (int w = 0; w < dm.W; w++) {
+      uint32_t t = (w * dm.c < 128 ? big_raw_digit(k6[h], w, dm.c) : 0u) + carry;
+      carry = t > (uint32_t)dm.M ? 1u : 0u;
+      if (w != next_local) continue;  // uniform: every lane walks the same windows
+      int32_t d = carry ? (int32_t)t - (int32_t)(2 * dm.M) : (int32_t)t;
+      uint32_t key = 0xffffffffu;
+      if (live && d != 0) key = (uint32_t)j * (uint32_t)dm.M + (uint32_t)(d < 0 ? -d : d) - 1u;
+      // warp-aggregated atomic: one add per distinct key in the warp (degenerate inputs put
+      // all 32 lanes on one counter)
+      uint32_t peers = __match_any_sync(0xffffffffu, key);
+      uint32_t leader = __ffs(peers) - 1;
+      uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+      uint32_t base = 0;
+      if (key != 0xffffffffu && lane == leader) base = atomicAdd(&counters[key], (uint32_t)__popc(peers));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (PASS == 1 && key != 0xffffffffu)
+        entries[offsets[key] + base + rank] =
+            ((uint32_t)i + (h ? (uint32_t)n : 0u)) | (((d < 0) != neg[h]) ? 0x80000000u : 0u);
+      next_local += dm.wstep;
+      j++;
+    }
   }
 }
 
@@ -188,12 +220,12 @@ cudaError_t launch_exclusive_scan(uint32_t* counts, uint32_t n, uint32_t* bsum, 
 // ---------------------------------------------------------------- large buckets
 // meta[0] = number of large buckets, meta[1] = number of slices
 __global__ void __launch_bounds__(256)
-k_big_mark_large(const uint32_t* __restrict__ offsets, uint32_t nb, uint32_t* __restrict__ meta,
-                 BigLargeRec* __restrict__ large, BigSliceRec* __restrict__ slices) {
+k_big_mark_large(const uint32_t* __restrict__ offsets, uint32_t nb, uint32_t large_thresh,
+                 uint32_t* __restrict__ meta, BigLargeRec* __restrict__ large, BigSliceRec* __restrict__ slices) {
   uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
   uint32_t s = offsets[b], cnt = offsets[b + 1] - s;
-  if (cnt <= kBigLargeBucket) return;
+  if (cnt <= large_thresh) return;
   uint32_t ns = (cnt + kBigSliceLen - 1) / kBigSliceLen;
   uint32_t li = atomicAdd(&meta[0], 1u);
   uint32_t sf = atomicAdd(&meta[1], ns);
@@ -222,9 +254,9 @@ __device__ __forceinline__ void big_cta_tree(G1Xyzz* sh, const G1Xyzz& mine) {
 }
 
 __global__ void __launch_bounds__(kBigCtaThreads)
-k_big_slice(const G1Affine* __restrict__ points, const uint32_t* __restrict__ entries,
-            const uint32_t* __restrict__ meta, const BigSliceRec* __restrict__ slices,
-            G1Xyzz* __restrict__ slice_out) {
+k_big_slice(const G1Affine* __restrict__ points, const G1Affine* __restrict__ phi, uint32_t n,
+            const uint32_t* __restrict__ entries, const uint32_t* __restrict__ meta,
+            const BigSliceRec* __restrict__ slices, G1Xyzz* __restrict__ slice_out) {
   __shared__ G1Xyzz sh[kBigCtaThreads];
   const uint32_t nslices = meta[1];
 #pragma unroll 1
@@ -235,7 +267,8 @@ k_big_slice(const G1Affine* __restrict__ points, const uint32_t* __restrict__ en
 #pragma unroll 1
     for (uint32_t t = threadIdx.x; t < r.count; t += kBigCtaThreads) {
       uint32_t en = entries[r.first + t];
-      G1Affine q = points[en & 0x7fffffffu];
+      uint32_t pi = en & 0x7fffffffu;
+      G1Affine q = pi < n ? points[pi] : phi[pi - n];
       if (en >> 31) FpM::neg(q.y, q.y);
       xyzz_add_mixed(acc, acc, q);
     }
@@ -266,20 +299,51 @@ k_big_large_finish(const uint32_t* __restrict__ meta, const BigLargeRec* __restr
   }
 }
 
+// ---------------------------------------------------------------- size-ordered schedule
+// Buckets are handed to threads in order of decreasing length (a counting sort on the
+// length), so the 32 buckets of a warp have (almost) the same trip count and no lane waits
+// for a longer neighbour.  Lengths above kBigLargeBucket count as 0 (slice path).
+__device__ __forceinline__ uint32_t big_size_bin(const uint32_t* __restrict__ offsets, uint32_t b, uint32_t large_thresh) {
+  uint32_t cnt = offsets[b + 1] - offsets[b];
+  if (cnt > large_thresh) cnt = 0;
+  return large_thresh - cnt;  // bin 0 = longest
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(256)
+k_big_size_sort(const uint32_t* __restrict__ offsets, uint32_t nb, uint32_t large_thresh,
+                uint32_t* __restrict__ bin_counters, const uint32_t* __restrict__ bin_offsets,
+                uint32_t* __restrict__ order) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31;
+  uint32_t bin = b < nb ? big_size_bin(offsets, b, large_thresh) : 0xffffffffu;
+  uint32_t peers = __match_any_sync(0xffffffffu, bin);
+  uint32_t leader = __ffs(peers) - 1;
+  uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+  uint32_t base = 0;
+  if (bin != 0xffffffffu && lane == leader) base = atomicAdd(&bin_counters[bin], (uint32_t)__popc(peers));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (PASS == 1 && bin != 0xffffffffu) order[bin_offsets[bin] + base + rank] = b;
+}
+
 // ---------------------------------------------------------------- bucket accumulation
 __global__ void __launch_bounds__(128, 3)
-k_big_accum(const G1Affine* __restrict__ points, const uint32_t* __restrict__ entries,
-            const uint32_t* __restrict__ offsets, uint32_t nb, G1Xyzz* __restrict__ buckets) {
-  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= nb) return;
+k_big_accum(const G1Affine* __restrict__ points, const G1Affine* __restrict__ phi, uint32_t n,
+            const uint32_t* __restrict__ entries, const uint32_t* __restrict__ offsets,
+            const uint32_t* __restrict__ order, uint32_t nb, uint32_t large_thresh,
+            G1Xyzz* __restrict__ buckets) {
+  uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= nb) return;
+  const uint32_t b = order[tid];
   uint32_t s = offsets[b], e = offsets[b + 1];
   G1Xyzz acc;
   xyzz_set_inf(acc);
-  if (e - s <= kBigLargeBucket) {
+  if (e - s <= large_thresh) {
 #pragma unroll 1
     for (uint32_t t = s; t < e; t++) {
       uint32_t en = entries[t];
-      G1Affine q = points[en & 0x7fffffffu];
+      uint32_t pi = en & 0x7fffffffu;
+      G1Affine q = pi < n ? points[pi] : phi[pi - n];
       if (en >> 31) FpM::neg(q.y, q.y);
       xyzz_add_mixed(acc, acc, q);
     }
@@ -386,38 +450,43 @@ __global__ void k_big_combine(const G1Jac* __restrict__ in, int n, G1Jac* __rest
 }
 
 // ---------------------------------------------------------------- host side
+// window width by size, measured on B200 (tools/msm_sweep.py --scan-c, profiles/)
 int big_msm_pick_c(size_t n) {
   int lg = 0;
   while (((size_t)1 << (lg + 1)) <= n) lg++;
-  int c = lg <= 10 ? 8 : lg <= 12 ? 9 : lg <= 13 ? 10 : lg <= 14 ? 11 : lg <= 15 ? 12 : lg <= 17 ? 13
-          : lg <= 18 ? 14 : lg <= 19 ? 15 : 16;
-  return c;
+  static const int table[] = {8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 11, 12, 12, 15, 15, 16, 16, 16, 16};
+  return lg <= 20 ? table[lg] : 16;
 }
 
 BigMsmDims big_msm_dims(size_t n, int c, int wfirst, int wstep) {
   BigMsmDims d;
   d.n = (int)n;
   d.c = c;
-  d.W = (256 + c - 1) / c;
+  d.W = (128 + c - 1) / c;  // windows over the 128-bit GLV halves
   d.M = 1 << (c - 1);
   d.wfirst = wfirst;
   d.wstep = wstep;
   d.nlocal = wfirst < d.W ? (d.W - wfirst + wstep - 1) / wstep : 0;
   d.nb = (uint32_t)d.nlocal * (uint32_t)d.M;
+  // a bucket longer than 8x the mean goes to the CTA-per-slice path instead of one thread
+  // (degenerate scalars, and the top window, which holds only 256 - c*(W-1) scalar bits)
+  size_t mean = 2 * n / (size_t)d.M + 1;
+  size_t lt = 8 * mean;
+  d.large = (uint32_t)(lt < 64 ? 64 : lt > kBigLargeBucket ? kBigLargeBucket : lt);
   return d;
 }
 
 static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct BigLayout {
-  size_t counts, offsets, bsum, meta, entries, buckets, large, slices, slice_out, red0, red1, total;
+  size_t counts, offsets, bsum, meta, entries, buckets, large, slices, slice_out, red0, red1, bins, bin_off, order, phi, total;
   uint32_t max_slices, max_large;
 };
 
 static BigLayout big_layout(const BigMsmDims& d) {
   BigLayout L;
-  size_t nent = (size_t)d.n * (size_t)d.nlocal;
-  L.max_large = (uint32_t)(nent / kBigLargeBucket + 1);
+  size_t nent = 2 * (size_t)d.n * (size_t)d.nlocal;
+  L.max_large = (uint32_t)(nent / d.large + 1);
   L.max_slices = (uint32_t)(nent / kBigSliceLen + L.max_large + 1);
   size_t o = 0;
   L.counts = o; o += al256(((size_t)d.nb + 1) * 4);
@@ -432,6 +501,10 @@ static BigLayout big_layout(const BigMsmDims& d) {
   size_t red = ((size_t)d.nb / 2 + (size_t)d.nlocal + 1) * sizeof(G1Xyzz);
   L.red0 = o; o += al256(red);
   L.red1 = o; o += al256(red);
+  L.bins = o; o += al256(((size_t)kBigLargeBucket + 2) * 4);
+  L.bin_off = o; o += al256(((size_t)kBigLargeBucket + 3) * 4);
+  L.order = o; o += al256(((size_t)d.nb + 1) * 4);
+  L.phi = o; o += al256(((size_t)d.n + 1) * sizeof(G1Affine));
   L.total = o;
   return L;
 }
@@ -453,6 +526,10 @@ cudaError_t launch_big_msm(const G1Affine* points, const Fr* scalars, const BigM
   BigSliceRec* slices = (BigSliceRec*)(base + L.slices);
   G1Xyzz* slice_out = (G1Xyzz*)(base + L.slice_out);
   G1Xyzz* red[2] = {(G1Xyzz*)(base + L.red0), (G1Xyzz*)(base + L.red1)};
+  uint32_t* bins = (uint32_t*)(base + L.bins);
+  uint32_t* bin_off = (uint32_t*)(base + L.bin_off);
+  uint32_t* order = (uint32_t*)(base + L.order);
+  G1Affine* phi = (G1Affine*)(base + L.phi);
 
   if (d.nlocal == 0 || d.n == 0) {  // this rank owns no window: partial sum = infinity
     G1Xyzz* one = red[0];
@@ -466,13 +543,20 @@ cudaError_t launch_big_msm(const G1Affine* points, const Fr* scalars, const BigM
   cudaMemsetAsync(counts, 0, ((size_t)nb + 1) * 4, st);
   cudaMemsetAsync(meta, 0, 256, st);
   const int gd = (d.n + 255) / 256;
+  k_big_phi<<<gd, 256, 0, st>>>(points, d.n, phi);
   k_big_digits<0><<<gd, 256, 0, st>>>(scalars, d.n, d, counts, nullptr, nullptr);
   cudaError_t se = launch_exclusive_scan(counts, nb, bsum, offsets, st);
   if (se != cudaSuccess) return se;
   k_big_digits<1><<<gd, 256, 0, st>>>(scalars, d.n, d, counts, offsets, entries);
-  k_big_mark_large<<<(nb + 255) / 256, 256, 0, st>>>(offsets, nb, meta, large, slices);
-  k_big_accum<<<(nb + 127) / 128, 128, 0, st>>>(points, entries, offsets, nb, buckets);
-  k_big_slice<<<sm_count * 4, kBigCtaThreads, 0, st>>>(points, entries, meta, slices, slice_out);
+  k_big_mark_large<<<(nb + 255) / 256, 256, 0, st>>>(offsets, nb, d.large, meta, large, slices);
+  const uint32_t nbins = d.large + 1;
+  cudaMemsetAsync(bins, 0, ((size_t)nbins + 1) * 4, st);
+  k_big_size_sort<0><<<(nb + 255) / 256, 256, 0, st>>>(offsets, nb, d.large, bins, nullptr, nullptr);
+  se = launch_exclusive_scan(bins, nbins, bsum, bin_off, st);
+  if (se != cudaSuccess) return se;
+  k_big_size_sort<1><<<(nb + 255) / 256, 256, 0, st>>>(offsets, nb, d.large, bins, bin_off, order);
+  k_big_accum<<<(nb + 127) / 128, 128, 0, st>>>(points, phi, (uint32_t)d.n, entries, offsets, order, nb, d.large, buckets);
+  k_big_slice<<<sm_count * 4, kBigCtaThreads, 0, st>>>(points, phi, (uint32_t)d.n, entries, meta, slices, slice_out);
   k_big_large_finish<<<sm_count, kBigCtaThreads, 0, st>>>(meta, large, slice_out, buckets);
   // bucket reduction
   int Lc = d.M < 16 ? d.M : 16;

@@ -82,7 +82,8 @@ void launch_msm_small(const G1Affine* points, const uint32_t* idx, const Fr* sca
 // wfirst, wfirst + wstep, ... (multi-GPU window partition).
 struct BigMsmDims {
   int n, c, W, M, wfirst, wstep, nlocal;
-  uint32_t nb;  // nlocal * M buckets
+  uint32_t nb;     // nlocal * M buckets
+  uint32_t large;  // buckets with more entries than this are summed by whole CTAs (slices)
 };
 constexpr size_t kBigMsmThreshold = 1024;  // cdl_g1_msm switches to the Pippenger path above this size
 int big_msm_pick_c(size_t n);

@@ -21,8 +21,8 @@ def test_partition_covers_every_window_once(pkg):
 
 
 def signed_digits(k, c):
-    """Restatement of k_big_digits: W = ceil(256 / c) digits in [-2^(c-1), 2^(c-1)]."""
-    W = (256 + c - 1) // c
+    """Restatement of k_big_digits: W = ceil(128 / c) digits in [-2^(c-1), 2^(c-1)] of a GLV half < 2^127."""
+    W = (128 + c - 1) // c
     M = 1 << (c - 1)
     out, carry = [], 0
     for w in range(W):
@@ -35,7 +35,7 @@ def signed_digits(k, c):
 
 def test_signed_digit_decomposition_reconstructs():
     random.seed(3)
-    ks = [0, 1, b.R - 1, b.R - 2, 2**254, 2**255 % b.R, (b.R - 1) // 2] + [random.randrange(b.R) for _ in range(200)]
+    ks = [0, 1, 2**127 - 1, 2**126, 2**127 - 2**64] + [random.randrange(2**127) for _ in range(200)]
     for c in range(2, 19):
         M = 1 << (c - 1)
         for k in ks:
