@@ -1,5 +1,6 @@
 // Elementwise batched point kernels: scalar multiplication / base folding and
 // Jacobian -> affine.
+#define CDL_FP_MUL_CALL 1  // one shared product body: the hot loops fit the instruction caches (mont.cuh)
 #include <cuda_runtime.h>
 #include "g1.cuh"
 #include "launch.h"

@@ -19,6 +19,7 @@
 //   4. combine  : binary tree over windows, level L doubles the upper operand
 //                 4*2^L times (252 doublings on the critical path, 6 adds).
 //   5. normalise: one inversion, affine result (+ optional compressed bytes).
+#define CDL_FP_MUL_CALL 1  // one shared product body: the hot loops fit the instruction caches (mont.cuh)
 #include "codec.cuh"
 #include "launch.h"
 

@@ -26,6 +26,7 @@
 // A rank of a multi-GPU job owns windows wfirst, wfirst + wstep, ... and returns
 // its partial sum already shifted, so the exchange is one all-gather of one point
 // per rank (k_big_combine adds them).
+#define CDL_FP_MUL_CALL 1  // one shared product body: the hot loops fit the instruction caches (mont.cuh)
 #include "launch.h"
 
 namespace cdl {

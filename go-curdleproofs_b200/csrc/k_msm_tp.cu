@@ -17,6 +17,7 @@
 //                 but runs at full lane efficiency across thousands of MSMs.
 #include <cstdlib>
 
+#define CDL_FP_MUL_CALL 1
 #include "codec.cuh"
 #include "launch.h"
 

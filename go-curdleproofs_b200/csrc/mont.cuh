@@ -102,7 +102,22 @@ struct Mont {
     for (int i = 0; i < N; i++) r[i] = borrow ? r[i] : t[i];
   }
 
-  static CDL_HD void mul(El& r, const El& a, const El& b) {
+  // Translation units that define CDL_FP_MUL_CALL route every product through one shared,
+  // non-inlined body (operands and result by value, in registers): a kernel whose hot loop
+  // would otherwise hold ten inlined copies of the 420-instruction product (~70 KB of
+  // SASS) then fits the instruction caches.
+#if defined(__CUDA_ARCH__) && defined(CDL_FP_MUL_CALL)
+  static __device__ __noinline__ El mul_call(El a, El b) {
+    El r;
+    mul_inline(r, a, b);
+    return r;
+  }
+  static CDL_HD void mul(El& r, const El& a, const El& b) { r = mul_call(a, b); }
+#else
+  static CDL_HD void mul(El& r, const El& a, const El& b) { mul_inline(r, a, b); }
+#endif
+
+  static CDL_HD void mul_inline(El& r, const El& a, const El& b) {
     uint32_t even[N], odd[N];
 #pragma unroll
     for (int i = 0; i < N; i += 2) {
