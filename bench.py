@@ -247,6 +247,8 @@ def gpu_main(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
+    # ranks of one box share its host cores (Fiat-Shamir work between launches)
+    os.environ.setdefault("CDL_HOST_THREADS", str(max(2, (os.cpu_count() or 1) // max(1, world))))
     pkg = importlib.import_module("go-curdleproofs_b200")
     ctx = pkg.Context(local)  # raises without a GPU / without the built library: no fallback
     if args.lanes:
@@ -354,7 +356,7 @@ def gpu_main(args):
                        "l2": "flushed between steps (256 MiB write)",
                        "value_definition": "proofs / device busy time = union of CUDA-event kernel intervals over all lanes "
                                            "(host Fiat-Shamir excluded)",
-                       "lanes": args.lanes or 4,
+                       "lanes": args.lanes or 4, "host_threads_cap": int(os.environ.get("CDL_HOST_THREADS", "0")),
                        "device": info["name"], "sm_count": info["sm_count"]},
             "e2e": {"value": total_proofs / wall_max, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h,
@@ -395,9 +397,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="independent Whisk round trips per GPU per step")
+    ap.add_argument("--batch", type=int, default=2048, help="independent Whisk round trips per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--lanes", type=int, default=0, help="concurrent sub-batches per GPU (0 = library default)")
+    ap.add_argument("--lanes", type=int, default=8, help="concurrent sub-batches per GPU (0 = library default)")
     ap.add_argument("--no-msm", action="store_true", help="skip the standalone MSM sweep")
     ap.add_argument("--msm-sizes", default="", help="comma separated log2 sizes for the MSM sweep")
     args = ap.parse_args()

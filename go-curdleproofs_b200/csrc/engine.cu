@@ -3,6 +3,9 @@
 
 #include <algorithm>
 #include <array>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 using cdl::ElemOp;
@@ -40,10 +43,27 @@ Layout::Layout(uint32_t ell_) {
 // a lane engine shares the host cores with its sibling lanes
 Engine::Engine(cdl_ctx* ctx)
     : ctx_(ctx),
-      pool_(ctx->parent ? std::max(2u, std::min(32u, std::thread::hardware_concurrency() / 2))
-                        : std::max(1u, std::min(64u, std::thread::hardware_concurrency()))) {}
+      pool_(host_threads(ctx->parent != nullptr)) {}
+
+// CDL_HOST_THREADS caps the host cores one context may use (several ranks on one box share them)
+unsigned Engine::host_threads(bool lane) {
+  unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  if (const char* e = getenv("CDL_HOST_THREADS")) {
+    int v = atoi(e);
+    if (v >= 1) hw = std::min(hw, (unsigned)v);
+  }
+  return lane ? std::max(2u, std::min(32u, hw / 2)) : std::max(1u, std::min(64u, hw));
+}
+
+double Engine::now() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 Engine::~Engine() {
+  if (getenv("CDL_PROFILE"))
+    fprintf(stderr, "[cdl profile] engine %p (lane %d): total %.1f ms = parallel host %.1f + gpu stages %.1f (staging copies %.1f) + serial host %.1f\n",
+            (void*)this, ctx_->parent ? 1 : 0, prof.total * 1e3, prof.par * 1e3, prof.gpu * 1e3, prof.copy * 1e3,
+            (prof.total - prof.par - prof.gpu) * 1e3);
   cudaSetDevice(ctx_->device);
   if (d_pool_) cudaFree(d_pool_);
   if (d_win_) cudaFree(d_win_);
@@ -158,7 +178,17 @@ int32_t Engine::set_infinity(uint32_t dst, size_t count) {
   return CDL_OK;
 }
 
+namespace {
+struct ProfScope {
+  double& acc;
+  double t0;
+  explicit ProfScope(double& a) : acc(a), t0(Engine::now()) {}
+  ~ProfScope() { acc += Engine::now() - t0; }
+};
+}  // namespace
+
 int32_t Engine::compress(const std::vector<uint32_t>& src, std::vector<uint8_t>& out48) {
+  ProfScope ps(prof.gpu);
   size_t n = src.size();
   out48.resize(n * 48);
   if (!n) return CDL_OK;
@@ -178,6 +208,7 @@ int32_t Engine::compress(const std::vector<uint32_t>& src, std::vector<uint8_t>&
 }
 
 int32_t Engine::decompress(const uint8_t* enc48, const std::vector<uint32_t>& dst, std::vector<uint8_t>& status) {
+  ProfScope ps(prof.gpu);
   size_t n = dst.size();
   status.assign(n, 0);
   if (!n) return CDL_OK;
@@ -200,6 +231,7 @@ int32_t Engine::decompress(const uint8_t* enc48, const std::vector<uint32_t>& ds
 }
 
 int32_t Engine::run_msm(MsmStage& st) {
+  ProfScope ps(prof.gpu);
   size_t nt = st.tasks.size(), nterm = st.idx.size();
   st.out48.resize(nt * 48);
   if (!nt) return CDL_OK;
@@ -209,9 +241,12 @@ int32_t Engine::run_msm(MsmStage& st) {
   if ((rc = reserve(s_idx_, (nterm + 1) * 4)) || (rc = reserve(s_sc_, (nterm + 1) * 32)) ||
       (rc = reserve(s_task_, nt * sizeof(MsmTask))) || (rc = reserve(s_out_, nt * 48)))
     return rc;
-  memcpy(s_idx_.h, st.idx.data(), nterm * 4);
-  memcpy(s_sc_.h, st.sc.data(), nterm * 32);
-  memcpy(s_task_.h, st.tasks.data(), nt * sizeof(MsmTask));
+  {
+    ProfScope pc(prof.copy);
+    memcpy(s_idx_.h, st.idx.data(), nterm * 4);
+    memcpy(s_sc_.h, st.sc.data(), nterm * 32);
+    memcpy(s_task_.h, st.tasks.data(), nt * sizeof(MsmTask));
+  }
   CDL_CUDA(ctx_, cudaMemcpyAsync(s_idx_.d, s_idx_.h, nterm * 4, cudaMemcpyHostToDevice, ctx_->stream));
   CDL_CUDA(ctx_, cudaMemcpyAsync(s_sc_.d, s_sc_.h, nterm * 32, cudaMemcpyHostToDevice, ctx_->stream));
   CDL_CUDA(ctx_, cudaMemcpyAsync(s_task_.d, s_task_.h, nt * sizeof(MsmTask), cudaMemcpyHostToDevice, ctx_->stream));
@@ -260,6 +295,7 @@ int32_t Engine::run_msm(MsmStage& st) {
 }
 
 int32_t Engine::run_elem(const std::vector<ElemOp>& ops, const std::vector<Fr>& sc) {
+  ProfScope ps(prof.gpu);
   size_t n = ops.size();
   if (!n) return CDL_OK;
   int32_t rc;
@@ -314,6 +350,7 @@ inline bool is_inf_enc(const uint8_t* e) { return memcmp(e, kInfEnc, 48) == 0; }
 int32_t Engine::shuffle_permute_commit(const Layout& L, uint32_t B, const std::vector<std::vector<uint32_t>>& perms,
                                        const std::vector<Fr>& ks, std::vector<cdl_rand*>& rands,
                                        std::vector<std::vector<Fr>>& rs_m) {
+  ProfScope ptot(prof.total);
   const uint32_t ell = L.ell;
   // Ts[i] = k * Rs[perm[i]], Us[i] = k * Ss[perm[i]]   (common/util.go:55-66)
   std::vector<ElemOp> ops((size_t)B * 2 * ell);
@@ -407,6 +444,7 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
                       const std::vector<Fr>& ks, const std::vector<std::vector<Fr>>& rs_m_in,
                       std::vector<cdl_rand*>& rands, std::vector<std::vector<uint8_t>>& proofs,
                       std::vector<int32_t>& status, std::vector<std::string>& errs, std::vector<uint8_t>& inst_enc) {
+  ProfScope ptot(prof.total);
   const uint32_t ell = L.ell, n = L.n, m = L.m;
   if (n != (1u << m)) return ctx_->fail(CDL_ERR_PROTOCOL, "cs and ds are not a power of two (ell + 4 = %u)", n);
   int32_t rc;
@@ -425,7 +463,7 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
   }
   if ((rc = compress(src, inst_enc))) return rc;
   const size_t per_inst = (size_t)(4 * ell + 1) * 48;
-  pool_.parallel_for(B, [&](size_t b) {
+  par(B, [&](size_t b) {
     ProveState& s = *S[b];
     const uint8_t* e = inst_enc.data() + b * per_inst;
     s.tr.append_points("curdleproofs_step1", e, 4 * ell + 1);
@@ -440,7 +478,7 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
   // ---- A = <perm_as, Gs> + <rs_a', Hs>   (:72-79)
   {
     StageBuilder sb(st, B, ell + 2, 1);
-    pool_.parallel_for(B, [&](size_t b) {
+    par(B, [&](size_t b) {
       ProveState& s = *S[b];
       MsmSlice sl = sb.slice((uint32_t)b);
       sl.begin(L.base((uint32_t)b) + L.A);
@@ -453,7 +491,7 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
   }
 
   // ---- same-permutation argument, step 1-2 (samepermutationargument.go:44-80)
-  pool_.parallel_for(B, [&](size_t b) {
+  par(B, [&](size_t b) {
     ProveState& s = *S[b];
     const uint8_t* M_enc = inst_enc.data() + b * per_inst + (size_t)4 * ell * 48;
     s.tr.append_points("same_perm_step1", s.A, 1);
@@ -492,7 +530,7 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
 
   // ---- grand-product argument (grandproductargument.go:52-92)
   std::vector<Fr> gp_alpha(B), gp_beta(B);
-  pool_.parallel_for(B, [&](size_t b) {
+  par(B, [&](size_t b) {
     ProveState& s = *S[b];
     s.tr.append_points("gprod_step1", s.Bp, 1);
     s.tr.append_scalar("gprod_step1", s.p);
@@ -504,7 +542,7 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
   });
   {
     StageBuilder sb(st, B, n, 1);
-    pool_.parallel_for(B, [&](size_t b) {
+    par(B, [&](size_t b) {
       ProveState& s = *S[b];
       MsmSlice sl = sb.slice((uint32_t)b);
       sl.begin(L.base((uint32_t)b) + L.scratch);
@@ -521,7 +559,7 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
     // Gs'[i] = beta^-(i+1) Gs[i], Hs'[i] = beta^-(ell+1) Hs[i]  (:94-103) -> Gp; G = Gs || Hs
     std::vector<ElemOp> ops((size_t)B * n);
     std::vector<Fr> sc((size_t)B * (ell + 1));
-    pool_.parallel_for(B, [&](size_t b) {
+    par(B, [&](size_t b) {
       ProveState& s = *S[b];
       r_b_plus_alpha[b].resize(kBlinders);
       for (uint32_t i = 0; i < kBlinders; i++) r_b_plus_alpha[b][i] = fr_add(s.rs_b[i], gp_alpha[b]);
@@ -552,7 +590,7 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
   std::vector<std::array<uint8_t, 48>> D_enc(B);
   {
     StageBuilder sb(st, B, 5 * n + 1, 5);
-    pool_.parallel_for(B, [&](size_t b) {
+    par(B, [&](size_t b) {
       ProveState& s = *S[b];
       const Fr& beta = gp_beta[b];
       const Fr& alpha = gp_alpha[b];
@@ -610,7 +648,7 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
     }
   }
   // ---- inner-product argument (innerproductargument.go:74-188)
-  pool_.parallel_for(B, [&](size_t b) {
+  par(B, [&](size_t b) {
     ProveState& s = *S[b];
     s.tr.append_points("ipa_step1", s.C, 1);
     s.tr.append_points("ipa_step1", D_enc[b].data(), 1);
@@ -626,7 +664,7 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
   });
   for (uint32_t half = n / 2; half >= 1; half /= 2) {
     StageBuilder sb(st, B, 4 * half + 2, 4);
-    pool_.parallel_for(B, [&](size_t b) {
+    par(B, [&](size_t b) {
       ProveState& s = *S[b];
       uint32_t base = L.base((uint32_t)b);
       const Fr *c_L = s.cs.data(), *c_R = s.cs.data() + half, *d_L = s.ds.data(), *d_R = s.ds.data() + half;
@@ -649,7 +687,7 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
     if ((rc = run_msm(st))) return rc;
     std::vector<ElemOp> ops(half > 1 ? (size_t)B * 2 * (half) : 0);
     std::vector<Fr> sc((size_t)B * 2);
-    pool_.parallel_for(B, [&](size_t b) {
+    par(B, [&](size_t b) {
       ProveState& s = *S[b];
       const uint8_t *lc = sb.out((uint32_t)b, 0), *ld = sb.out((uint32_t)b, 1), *rcc = sb.out((uint32_t)b, 2), *rd = sb.out((uint32_t)b, 3);
       s.L_C.insert(s.L_C.end(), lc, lc + 48);
@@ -699,7 +737,7 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
       if ((rc = copy_points(base + L.Tp + ell + 2, L.H, 1))) return rc;    // T' = Ts || 0 || 0 || H || 0
       if ((rc = copy_points(base + L.Up + ell + 3, L.H, 1))) return rc;    // U' = Us || 0 || 0 || 0 || H
     }
-    pool_.parallel_for(B, [&](size_t b) {
+    par(B, [&](size_t b) {
       ProveState& s = *S[b];
       Rand& rand = rands[b]->r;
       s.r_t = rand.get_fr();
@@ -745,7 +783,7 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
       sl.end();
     });
     if ((rc = run_msm(st))) return rc;
-    pool_.parallel_for(B, [&](size_t b) {
+    par(B, [&](size_t b) {
       ProveState& s = *S[b];
       auto out = [&](uint32_t t) { return sb.out((uint32_t)b, t); };
       memcpy(s.R, out(0), 48); memcpy(s.S, out(1), 48);
@@ -788,7 +826,7 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
   // ---- same-multiscalar rounds (samemultiscalarargument.go:85-140)
   for (uint32_t half = n / 2; half >= 1; half /= 2) {
     StageBuilder sb(st, B, 6 * half, 6);
-    pool_.parallel_for(B, [&](size_t b) {
+    par(B, [&](size_t b) {
       ProveState& s = *S[b];
       uint32_t base = L.base((uint32_t)b);
       const Fr *x_L = s.x.data(), *x_R = s.x.data() + half;
@@ -808,7 +846,7 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
     if ((rc = run_msm(st))) return rc;
     std::vector<ElemOp> ops(half > 1 ? (size_t)B * 3 * half : 0);
     std::vector<Fr> sc(B);
-    pool_.parallel_for(B, [&](size_t b) {
+    par(B, [&](size_t b) {
       ProveState& s = *S[b];
       std::vector<uint8_t>* dstv[6] = {&s.L_A, &s.L_T, &s.L_U, &s.R_A, &s.R_T, &s.R_U};
       for (int t = 0; t < 6; t++) {

@@ -64,6 +64,7 @@ struct Wire {
 int32_t Engine::verify(const Layout& L, uint32_t B, const cdl_crs* crs, std::vector<ParsedProof>& pp,
                        std::vector<cdl_rand*>& rands, std::vector<int32_t>& verdict, std::vector<int32_t>& status,
                        std::vector<std::string>& errs) {
+  struct Tot { double& a; double t0; ~Tot() { a += Engine::now() - t0; } } ptot{prof.total, now()};
   const uint32_t ell = L.ell, n = L.n;
   int32_t rc;
   verdict.assign(B, 0);
@@ -100,7 +101,7 @@ int32_t Engine::verify(const Layout& L, uint32_t B, const cdl_crs* crs, std::vec
 
   // ---- transcript up to the grand-product challenges (curdleproof.go:213-223,
   // samepermutationargument.go:118-130, grandproductargument.go:219-232)
-  pool_.parallel_for(B, [&](size_t b) {
+  par(B, [&](size_t b) {
     VState& s = *S[b];
     if (s.failed) return;
     const ParsedProof& q = pp[b];
@@ -155,7 +156,7 @@ int32_t Engine::verify(const Layout& L, uint32_t B, const cdl_crs* crs, std::vec
   std::vector<std::vector<Fr>> t_sc(B);
   std::vector<std::vector<uint32_t>> t_cnt(B);  // term count of each of the instance's tasks
   std::vector<uint8_t> have_big(B, 0);
-  pool_.parallel_for(B, [&](size_t b) {
+  par(B, [&](size_t b) {
     VState& s = *S[b];
     if (s.failed) return;
     const ParsedProof& q = pp[b];

@@ -143,6 +143,21 @@ class Engine {
     double bytes[4] = {};
   } stats;
   static double msm_algorithmic_modmul(uint64_t terms);
+  // CDL_PROFILE=1: wall-clock split of the protocol calls, printed when the engine is destroyed
+  struct HostProf {
+    double par = 0;    // inside parallel_for sections (per-proof host work)
+    double gpu = 0;    // inside GPU stage calls (staging copies + launch + wait)
+    double copy = 0;   // of which: filling the pinned staging buffers
+    double total = 0;  // prove + verify + shuffle_permute_commit calls
+  } prof;
+  template <class F>
+  void par(size_t n, F&& f) {
+    double t0 = now();
+    pool_.parallel_for(n, std::function<void(size_t)>(std::forward<F>(f)));
+    prof.par += now() - t0;
+  }
+  static double now();
+  static unsigned host_threads(bool lane);
 
  private:
   cdl_ctx* ctx_;

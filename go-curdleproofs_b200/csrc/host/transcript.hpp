@@ -14,8 +14,9 @@
 
 namespace cdlh {
 
-inline uint64_t rol64(uint64_t v, int n) { return n ? (v << n) | (v >> (64 - n)) : v; }
+inline uint64_t rol64(uint64_t v, int n) { return (v << n) | (v >> (64 - n)); }  // n in 1..63
 
+// one round fully unrolled on 25 local lanes (generated straight-line code: theta, rho+pi, chi, iota)
 inline void keccak_f1600(uint64_t a[25]) {
   static const uint64_t RC[24] = {
       0x0000000000000001ull, 0x0000000000008082ull, 0x800000000000808aull, 0x8000000080008000ull,
@@ -24,18 +25,71 @@ inline void keccak_f1600(uint64_t a[25]) {
       0x000000008000808bull, 0x800000000000008bull, 0x8000000000008089ull, 0x8000000000008003ull,
       0x8000000000008002ull, 0x8000000000000080ull, 0x000000000000800aull, 0x800000008000000aull,
       0x8000000080008081ull, 0x8000000000008080ull, 0x0000000080000001ull, 0x8000000080008008ull};
-  static const int ROT[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
+  uint64_t s0 = a[0], s1 = a[1], s2 = a[2], s3 = a[3], s4 = a[4], s5 = a[5], s6 = a[6], s7 = a[7], s8 = a[8], s9 = a[9], s10 = a[10], s11 = a[11], s12 = a[12], s13 = a[13], s14 = a[14], s15 = a[15], s16 = a[16], s17 = a[17], s18 = a[18], s19 = a[19], s20 = a[20], s21 = a[21], s22 = a[22], s23 = a[23], s24 = a[24];
   for (int rnd = 0; rnd < 24; rnd++) {
-    uint64_t c[5], d[5], b[25];
-    for (int x = 0; x < 5; x++) c[x] = a[x] ^ a[x + 5] ^ a[x + 10] ^ a[x + 15] ^ a[x + 20];
-    for (int x = 0; x < 5; x++) d[x] = c[(x + 4) % 5] ^ rol64(c[(x + 1) % 5], 1);
-    for (int i = 0; i < 25; i++) a[i] ^= d[i % 5];
-    for (int x = 0; x < 5; x++)
-      for (int y = 0; y < 5; y++) b[y + 5 * ((2 * x + 3 * y) % 5)] = rol64(a[x + 5 * y], ROT[x + 5 * y]);
-    for (int x = 0; x < 5; x++)
-      for (int y = 0; y < 5; y++) a[x + 5 * y] = b[x + 5 * y] ^ (~b[(x + 1) % 5 + 5 * y] & b[(x + 2) % 5 + 5 * y]);
-    a[0] ^= RC[rnd];
+    const uint64_t c0 = s0 ^ s5 ^ s10 ^ s15 ^ s20;
+    const uint64_t c1 = s1 ^ s6 ^ s11 ^ s16 ^ s21;
+    const uint64_t c2 = s2 ^ s7 ^ s12 ^ s17 ^ s22;
+    const uint64_t c3 = s3 ^ s8 ^ s13 ^ s18 ^ s23;
+    const uint64_t c4 = s4 ^ s9 ^ s14 ^ s19 ^ s24;
+    const uint64_t d0 = c4 ^ rol64(c1, 1);
+    const uint64_t d1 = c0 ^ rol64(c2, 1);
+    const uint64_t d2 = c1 ^ rol64(c3, 1);
+    const uint64_t d3 = c2 ^ rol64(c4, 1);
+    const uint64_t d4 = c3 ^ rol64(c0, 1);
+    const uint64_t b0 = s0 ^ d0;
+    const uint64_t b16 = rol64(s5 ^ d0, 36);
+    const uint64_t b7 = rol64(s10 ^ d0, 3);
+    const uint64_t b23 = rol64(s15 ^ d0, 41);
+    const uint64_t b14 = rol64(s20 ^ d0, 18);
+    const uint64_t b10 = rol64(s1 ^ d1, 1);
+    const uint64_t b1 = rol64(s6 ^ d1, 44);
+    const uint64_t b17 = rol64(s11 ^ d1, 10);
+    const uint64_t b8 = rol64(s16 ^ d1, 45);
+    const uint64_t b24 = rol64(s21 ^ d1, 2);
+    const uint64_t b20 = rol64(s2 ^ d2, 62);
+    const uint64_t b11 = rol64(s7 ^ d2, 6);
+    const uint64_t b2 = rol64(s12 ^ d2, 43);
+    const uint64_t b18 = rol64(s17 ^ d2, 15);
+    const uint64_t b9 = rol64(s22 ^ d2, 61);
+    const uint64_t b5 = rol64(s3 ^ d3, 28);
+    const uint64_t b21 = rol64(s8 ^ d3, 55);
+    const uint64_t b12 = rol64(s13 ^ d3, 25);
+    const uint64_t b3 = rol64(s18 ^ d3, 21);
+    const uint64_t b19 = rol64(s23 ^ d3, 56);
+    const uint64_t b15 = rol64(s4 ^ d4, 27);
+    const uint64_t b6 = rol64(s9 ^ d4, 20);
+    const uint64_t b22 = rol64(s14 ^ d4, 39);
+    const uint64_t b13 = rol64(s19 ^ d4, 8);
+    const uint64_t b4 = rol64(s24 ^ d4, 14);
+    s0 = b0 ^ (~b1 & b2);
+    s1 = b1 ^ (~b2 & b3);
+    s2 = b2 ^ (~b3 & b4);
+    s3 = b3 ^ (~b4 & b0);
+    s4 = b4 ^ (~b0 & b1);
+    s5 = b5 ^ (~b6 & b7);
+    s6 = b6 ^ (~b7 & b8);
+    s7 = b7 ^ (~b8 & b9);
+    s8 = b8 ^ (~b9 & b5);
+    s9 = b9 ^ (~b5 & b6);
+    s10 = b10 ^ (~b11 & b12);
+    s11 = b11 ^ (~b12 & b13);
+    s12 = b12 ^ (~b13 & b14);
+    s13 = b13 ^ (~b14 & b10);
+    s14 = b14 ^ (~b10 & b11);
+    s15 = b15 ^ (~b16 & b17);
+    s16 = b16 ^ (~b17 & b18);
+    s17 = b17 ^ (~b18 & b19);
+    s18 = b18 ^ (~b19 & b15);
+    s19 = b19 ^ (~b15 & b16);
+    s20 = b20 ^ (~b21 & b22);
+    s21 = b21 ^ (~b22 & b23);
+    s22 = b22 ^ (~b23 & b24);
+    s23 = b23 ^ (~b24 & b20);
+    s24 = b24 ^ (~b20 & b21);
+    s0 ^= RC[rnd];
   }
+  a[0] = s0; a[1] = s1; a[2] = s2; a[3] = s3; a[4] = s4; a[5] = s5; a[6] = s6; a[7] = s7; a[8] = s8; a[9] = s9; a[10] = s10; a[11] = s11; a[12] = s12; a[13] = s13; a[14] = s14; a[15] = s15; a[16] = s16; a[17] = s17; a[18] = s18; a[19] = s19; a[20] = s20; a[21] = s21; a[22] = s22; a[23] = s23; a[24] = s24;
 }
 
 // SHAKE256 with an incremental squeeze (sha3.NewShake256: Write then Read)

@@ -91,8 +91,10 @@ k_msm_warp(const G1Affine* __restrict__ points, const MsmRec* __restrict__ rec, 
   G1Xyzz run, acc;
   xyzz_set_inf(run);
   xyzz_set_inf(acc);
+  // buckets above the highest non-empty one contribute nothing: start there (short chunks in the
+  // late folding rounds touch one or two buckets per window)
 #pragma unroll 1
-  for (int a = 7; a >= 0; a--) {
+  for (int a = nonempty ? 31 - __clz(nonempty) : -1; a >= 0; a--) {
     if ((nonempty >> a) & 1u) {
       G1Xyzz b = bk[a];
       xyzz_add(run, run, b);
