@@ -305,10 +305,46 @@ def gpu_main(args):
     sampler.stop_flag.set()
     sampler.join(timeout=2)
     assert status == [0] * B and ok == [1] * B and st == [0] * B, "timed round trip failed"
-    stats = ctx.engine_stats()
+    stats_timed = ctx.engine_stats()
     launches = ctx.launch_count() - l0
-    dev_ms = sum(v["ms"] for v in stats.values())
     busy_ms = ctx.engine_busy_ms()
+    # roofline pass: the same step with ONE lane, so that the CUDA-event interval of a kernel is
+    # its own duration (with several lanes the streams share the GPU and every interval also
+    # contains the other lanes' kernels); one untimed warm-up, then one measured step
+    ctx.set_lanes(1)
+    step()
+    ctx.engine_stats(reset=True)
+    status, ok, st = step()
+    torch.cuda.synchronize()
+    assert status == [0] * B and ok == [1] * B and st == [0] * B, "roofline-pass round trip failed"
+    stats = ctx.engine_stats()
+    ctx.set_lanes(args.lanes or 4)
+    dev_ms = sum(v["ms"] for v in stats.values())
+    # config 4 of BASELINE.json: batched verification only, every 8th instance mutated (pre / post
+    # trackers swapped) so that reject paths are exercised; wall clock through the C ABI
+    tb = ELL * 96
+    post, proofs, status = ctx.whisk_generate_shuffle_proof_batch(crs, pre, [pkg.Rand((rank << 40) | (77 << 20) | i) for i in range(B)])
+    pre_m, post_m = bytearray(pre), bytearray(post)
+    for i in range(0, B, 8):
+        pre_m[i * tb:(i + 1) * tb], post_m[i * tb:(i + 1) * tb] = post[i * tb:(i + 1) * tb], pre[i * tb:(i + 1) * tb]
+    pre_m, post_m = bytes(pre_m), bytes(post_m)
+    vt = []
+    verdict_ok = True
+    for it in range(3):  # first pass is the warm-up
+        barrier()
+        t1 = time.perf_counter()
+        vok, vst = ctx.whisk_is_valid_shuffle_proof_batch(crs, pre_m, post_m, proofs,
+                                                          [pkg.Rand((rank << 40) | (78 << 20) | i) for i in range(B)])
+        torch.cuda.synchronize()
+        vt.append(time.perf_counter() - t1)
+        verdict_ok = verdict_ok and vok == [0 if i % 8 == 0 else 1 for i in range(B)] and vst == [0] * B
+    tv = torch.tensor([sum(vt[1:])], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(tv, op=dist.ReduceOp.MAX)
+    verify_only = {"workload": "batched IsValidWhiskShuffleProof, n=128, every 8th instance mutated",
+                   "value": world * B * 2 / float(tv[0]), "unit": "verifications/s", "batch_per_gpu": B,
+                   "timing": "wall clock through the C ABI with host buffers, 2 batches after 1 warm-up",
+                   "verdicts": "as expected" if verdict_ok else "MISMATCH"}
     msm = None
     if not args.no_msm:
         msm = msm_sweep(ctx, pkg, [16, 20, 22] if not args.msm_sizes else [int(x) for x in args.msm_sizes.split(",")],
@@ -332,9 +368,26 @@ def gpu_main(args):
         n_launch = max(1, tk["launches"])
         avg_ms = tk["ms"] / n_launch
         achieved = tk["modmul"] / (tk["ms"] * 1e-3) if tk["ms"] else 0.0
+        traffic = None
+        try:  # dram bytes per launch of the dominant kernel class from an ncu capture of this command
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            if tj.get("batch") == B:
+                traffic = tj.get(top)
+        except Exception:
+            pass
+        timed = stats_timed[top]
         roofline = {
-            "bound": "int_alu", "kernel": top, "achieved": achieved / 1e9, "peak": peak_modmul / 1e9,
-            "unit": "Gmodmul/s", "frac": achieved / peak_modmul if peak_modmul else None, "traffic": None,
+            "bound": "int_alu", "kernel": top + (" (k_msm_recode + k_msm_warp + k_msm_chunk_sum + k_msm_combine_tp)"
+                                                 if top == "msm_small" else ""),
+            "achieved": achieved / 1e9, "peak": peak_modmul / 1e9,
+            "unit": "Gmodmul/s", "frac": achieved / peak_modmul if peak_modmul else None, "traffic": traffic,
+            "measured_in": "one extra step of the same batch with 1 lane, CUDA events on the launching stream "
+                           "(kernel intervals of concurrent lanes overlap and would count each other's time)",
+            "timed_region": {"lanes": args.lanes or 4, "launches": timed["launches"],
+                             "avg_launch_ms_overlapped": timed["ms"] / max(1, timed["launches"])},
+            "carry_chain_ceiling": "IMAD.WIDE.U32 with a carry issues at half rate on sm_100a (profiles/"
+                                   "r1_probe_instruction_rates.txt): a 32-bit-limb Montgomery product cannot exceed "
+                                   "frac 0.5",
             "peak_source": "measured live: IMAD.WIDE.U32 issue rate (cdl_int_peak kind 1, burst) / 300 per modmul",
             "avg_launch_ms": avg_ms, "launches": tk["launches"],
             "algorithmic_modmul_per_launch": tk["modmul"] / n_launch,
@@ -365,6 +418,7 @@ def gpu_main(args):
             "roofline": roofline,
             "clocks": sampler.summary(),
         }
+        line["verify_only"] = verify_only
         if msm is not None:
             line["msm"] = {"workload": "standalone G1 MSM, random points/scalars, device resident"
                                        + (f", windows dealt to {world} ranks + NCCL all-gather" if world > 1 else ""),

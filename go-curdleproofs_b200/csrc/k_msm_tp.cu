@@ -25,7 +25,31 @@ namespace cdl {
 
 constexpr int kTpWindows = 32;
 
-struct MsmRec {
+// Streaming (evict-first) loads for data a warp reads once — the recoded terms and the base
+// points — so that they do not push the warps' bucket arrays (local memory, re-read on every
+// addition) out of L2.
+template <class T>
+__device__ __forceinline__ T ld_stream8(const T* p) {
+  static_assert(sizeof(T) % 8 == 0, "8-byte granules");
+  T v;
+  const uint2* s = reinterpret_cast<const uint2*>(p);
+  uint2* d = reinterpret_cast<uint2*>(&v);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(T) / 8); i++) d[i] = __ldcs(s + i);
+  return v;
+}
+template <class T>
+__device__ __forceinline__ T ld_stream16(const T* p) {
+  static_assert(sizeof(T) % 16 == 0, "16-byte granules");
+  T v;
+  const uint4* s = reinterpret_cast<const uint4*>(p);
+  uint4* d = reinterpret_cast<uint4*>(&v);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(T) / 16); i++) d[i] = __ldcs(s + i);
+  return v;
+}
+
+struct alignas(8) MsmRec {
   uint32_t k1p[4];
   uint32_t k2p[4];
   uint32_t pidx;   // pool index of the base
@@ -49,7 +73,10 @@ __global__ void k_msm_recode(const uint32_t* __restrict__ idx, const Fr* __restr
   rec[t] = r;
 }
 
-__global__ void __launch_bounds__(128, 3)
+#ifndef CDL_WARP_MIN_CTAS
+#define CDL_WARP_MIN_CTAS 2
+#endif
+__global__ void __launch_bounds__(128, CDL_WARP_MIN_CTAS)
 k_msm_warp(const G1Affine* __restrict__ points, const MsmRec* __restrict__ rec, const MsmSub* __restrict__ subs,
            int nsub, G1Jac* __restrict__ win) {
   const int sub = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -62,8 +89,8 @@ k_msm_warp(const G1Affine* __restrict__ points, const MsmRec* __restrict__ rec, 
   fp_set_beta(beta);
 #pragma unroll 1
   for (uint32_t t = 0; t < s.term_cnt; t++) {
-    const MsmRec r = rec[s.term_off + t];
-    G1Affine p = points[r.pidx];
+    const MsmRec r = ld_stream8(rec + s.term_off + t);
+    G1Affine p = ld_stream16(points + r.pidx);
     if (aff_is_inf(p)) continue;  // uniform across the warp
     Fp bx;
     FpM::mul(bx, p.x, beta);
@@ -103,6 +130,95 @@ k_msm_warp(const G1Affine* __restrict__ points, const MsmRec* __restrict__ rec, 
   }
   G1Jac j;
   xyzz_to_jac(j, acc);
+  win[(size_t)w * nsub + sub] = j;
+}
+
+// Same walk with the 8 buckets of every lane in SHARED memory (Jacobian, 8 x 144 B x 32 lanes =
+// 36 KB per warp, one warp per CTA, six CTAs per SM): word i of bucket a of lane l lives at
+// sm[(a*36 + i)*32 + l], so every access is bank-conflict free whatever bucket each lane picks.
+// The private-array form above keeps the buckets in local memory, whose 49 KB per warp thrash
+// L1/L2 and show up as DRAM traffic hundreds of times the algorithmic bytes.
+template <class Bucket>
+struct SmemBucketOps;
+template <>
+struct SmemBucketOps<G1Jac> {
+  static __device__ __forceinline__ void from_affine(G1Jac& b, const G1Affine& q) { jac_from_affine(b, q); }
+  static __device__ __forceinline__ void add_mixed(G1Jac& b, const G1Affine& q) { jac_add_mixed(b, b, q); }
+  static __device__ __forceinline__ void add(G1Jac& r, const G1Jac& b) { jac_add(r, r, b); }
+  static __device__ __forceinline__ void set_inf(G1Jac& b) { jac_set_inf(b); }
+  static __device__ __forceinline__ void to_jac(G1Jac& j, const G1Jac& b) { j = b; }
+};
+template <>
+struct SmemBucketOps<G1Xyzz> {
+  static __device__ __forceinline__ void from_affine(G1Xyzz& b, const G1Affine& q) { xyzz_from_affine(b, q); }
+  static __device__ __forceinline__ void add_mixed(G1Xyzz& b, const G1Affine& q) { xyzz_add_mixed(b, b, q); }
+  static __device__ __forceinline__ void add(G1Xyzz& r, const G1Xyzz& b) { xyzz_add(r, r, b); }
+  static __device__ __forceinline__ void set_inf(G1Xyzz& b) { xyzz_set_inf(b); }
+  static __device__ __forceinline__ void to_jac(G1Jac& j, const G1Xyzz& b) { xyzz_to_jac(j, b); }
+};
+
+template <class Bucket>
+__global__ void __launch_bounds__(32)
+k_msm_warp_smem(const G1Affine* __restrict__ points, const MsmRec* __restrict__ rec,
+                const MsmSub* __restrict__ subs, int nsub, G1Jac* __restrict__ win) {
+  using Ops = SmemBucketOps<Bucket>;
+  constexpr int NW = sizeof(Bucket) / 4;
+  extern __shared__ uint32_t sm[];
+  const int sub = blockIdx.x;
+  const int w = threadIdx.x;
+  const MsmSub s = subs[sub];
+  uint32_t nonempty = 0;
+  Fp beta;
+  fp_set_beta(beta);
+#pragma unroll 1
+  for (uint32_t t = 0; t < s.term_cnt; t++) {
+    const MsmRec r = rec[s.term_off + t];
+    G1Affine p = points[r.pidx];
+    if (aff_is_inf(p)) continue;  // uniform across the warp
+    Fp bx;
+    FpM::mul(bx, p.x, beta);
+#pragma unroll 1
+    for (int h = 0; h < 2; h++) {
+      int d = glv_digit(h == 0 ? r.k1p : r.k2p, w);
+      if (d == 0) continue;
+      bool neg = (d < 0) != (((r.flags >> h) & 1u) != 0);
+      int a = (d < 0 ? -d : d) - 1;
+      G1Affine q;
+      q.x = h == 0 ? p.x : bx;
+      q.y = p.y;
+      if (neg) FpM::neg(q.y, q.y);
+      uint32_t* slot = sm + (size_t)a * NW * 32 + w;
+      Bucket b;
+      uint32_t* bw = reinterpret_cast<uint32_t*>(&b);
+      if (!((nonempty >> a) & 1u)) {
+        Ops::from_affine(b, q);
+        nonempty |= 1u << a;
+      } else {
+#pragma unroll
+        for (int i = 0; i < NW; i++) bw[i] = slot[i * 32];
+        Ops::add_mixed(b, q);
+      }
+#pragma unroll
+      for (int i = 0; i < NW; i++) slot[i * 32] = bw[i];
+    }
+  }
+  Bucket run, acc;
+  Ops::set_inf(run);
+  Ops::set_inf(acc);
+#pragma unroll 1
+  for (int a = nonempty ? 31 - __clz(nonempty) : -1; a >= 0; a--) {
+    if ((nonempty >> a) & 1u) {
+      Bucket b;
+      uint32_t* bw = reinterpret_cast<uint32_t*>(&b);
+      const uint32_t* slot = sm + (size_t)a * NW * 32 + w;
+#pragma unroll
+      for (int i = 0; i < NW; i++) bw[i] = slot[i * 32];
+      Ops::add(run, b);
+    }
+    Ops::add(acc, run);
+  }
+  G1Jac j;
+  Ops::to_jac(j, acc);
   win[(size_t)w * nsub + sub] = j;
 }
 
@@ -179,7 +295,22 @@ void launch_msm_tp(const G1Affine* points, const uint32_t* idx, const Fr* scalar
   G1Jac* win = (G1Jac*)((uint8_t*)scratch + rec_bytes);
   G1Jac* wsum = (G1Jac*)((uint8_t*)scratch + rec_bytes + win_bytes);
   if (nterm > 0) k_msm_recode<<<(nterm + 127) / 128, 128, 0, st>>>(idx, scalars, rec, nterm);
-  if (nsub > 0) k_msm_warp<<<(nsub + 3) / 4, 128, 0, st>>>(points, rec, subs, nsub, win);
+  static const int variant = [] {
+    const char* e = getenv("CDL_MSM_WARP");
+    return !e ? 0 : e[0] == 'j' ? 1 : e[0] == 'x' ? 2 : 0;
+  }();
+  if (nsub > 0) {
+    if (variant == 1) {
+      k_msm_warp_smem<G1Jac><<<nsub, 32, 8 * sizeof(G1Jac) * 32, st>>>(points, rec, subs, nsub, win);
+    } else if (variant == 2) {
+      static const cudaError_t attr = cudaFuncSetAttribute(k_msm_warp_smem<G1Xyzz>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                           (int)(8 * sizeof(G1Xyzz) * 32));
+      (void)attr;
+      k_msm_warp_smem<G1Xyzz><<<nsub, 32, 8 * sizeof(G1Xyzz) * 32, st>>>(points, rec, subs, nsub, win);
+    } else {
+      k_msm_warp<<<(nsub + 3) / 4, 128, 0, st>>>(points, rec, subs, nsub, win);
+    }
+  }
   k_msm_chunk_sum<<<(ntasks * kTpWindows + 127) / 128, 128, 0, st>>>(win, tasks, ntasks, nsub, wsum);
   k_msm_combine_tp<<<(ntasks + 63) / 64, 64, 0, st>>>(wsum, tasks, ntasks, out_aff, out_c48);
 }

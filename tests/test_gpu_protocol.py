@@ -184,3 +184,41 @@ def test_whisk_batch_matches_single_and_oracle_verdicts(ctx, pkg):
             assert bool(ok[i]) == want and (st[i] != 0) == err, i
     finally:
         P.set_backend(P.PyBackend())
+
+
+def test_lanes_give_the_same_bytes_and_verdicts(ctx, pkg):
+    """A batch cut into concurrent lanes (own stream / engine / host thread each) returns exactly
+    what one lane returns; every 8th instance is mutated (config 4 of BASELINE.json)."""
+    ell, B = 12, 100
+    crs = ctx.generate_crs(ell, pkg.Rand(0))
+    gen = aff_enc(b.G1_GEN)
+    pres = []
+    for i in range(4):
+        r = pkg.Rand(1000 + i)
+        ks, rs = [], []
+        for _ in range(ell):
+            ks.append(r.get_fr())
+            rs.append(r.get_fr())
+        rG = ctx.g1_scalar_mul_affine(gen * ell, b"".join(rs), broadcast=False)
+        krG = ctx.g1_scalar_mul_affine(rG, b"".join(ks), broadcast=False)
+        e1, e2 = ctx.g1_compress(rG), ctx.g1_compress(krG)
+        pres.append(b"".join(e1[48 * j:48 * j + 48] + e2[48 * j:48 * j + 48] for j in range(ell)))
+    pre = b"".join(pres[i % 4] for i in range(B))
+    out = {}
+    try:
+        for lanes in (1, 3):
+            ctx.set_lanes(lanes)
+            post, proofs, status = ctx.whisk_generate_shuffle_proof_batch(crs, pre, [pkg.Rand(3000 + i) for i in range(B)])
+            assert status == [0] * B
+            tb = ell * 96
+            pre_m, post_m = bytearray(pre), bytearray(post)
+            for i in range(0, B, 8):  # mutation: swap the instance's pre and post trackers
+                pre_m[i * tb:(i + 1) * tb], post_m[i * tb:(i + 1) * tb] = post[i * tb:(i + 1) * tb], pre[i * tb:(i + 1) * tb]
+            ok, st = ctx.whisk_is_valid_shuffle_proof_batch(crs, bytes(pre_m), bytes(post_m), proofs,
+                                                            [pkg.Rand(2000 + i) for i in range(B)])
+            assert st == [0] * B
+            assert ok == [0 if i % 8 == 0 else 1 for i in range(B)]
+            out[lanes] = (post, proofs, ok)
+    finally:
+        ctx.set_lanes(4)
+    assert out[1] == out[3]
