@@ -203,6 +203,12 @@ int32_t cdl_host_selftest(uint8_t* out32, const cdl_fr* a, const cdl_fr* b, cdl_
   Fr t1 = cdlh::fr_sub(cdlh::fr_add(cdlh::fr_mul(x, y), x), y);
   Fr r = cdlh::fr_mul(cdlh::fr_inv(t1), cdlh::fr_pow_u64(x, 5));
   memcpy(fr_out, &r, 32);
+  // the batched inversion must agree with the single one and keep zeros
+  std::vector<Fr> bi = cdlh::fr_batch_inv({x, t1, cdlh::FR_ZERO, y, t1});
+  if (!cdlh::fr_eq(bi[1], cdlh::fr_inv(t1)) || !cdlh::fr_eq(bi[4], bi[1]) || !cdlh::fr_is_zero(bi[2]) ||
+      !cdlh::fr_eq(bi[0], cdlh::fr_inv(x)) || !cdlh::fr_eq(bi[3], cdlh::fr_inv(y)))
+    return CDL_ERR_INTERNAL;
+  if (!cdlh::fr_is_zero(t1) && !cdlh::fr_eq(cdlh::fr_mul(t1, cdlh::fr_inv(t1)), cdlh::FR_ONE)) return CDL_ERR_INTERNAL;
   return CDL_OK;
 }
 

@@ -144,24 +144,87 @@ inline Fr fr_pow_u64(const Fr& a, uint64_t e) {  // fr.Element.Exp with a small 
   }
   return acc;
 }
-// fr.Element.Inverse: a^(r-2); Inverse(0) = 0
-inline Fr fr_inv(const Fr& a) {
-  uint64_t e[4] = {FR_MOD[0] - 2, FR_MOD[1], FR_MOD[2], FR_MOD[3]};
-  Fr acc = FR_ONE;
-  bool started = false;
-  for (int w = 3; w >= 0; w--)
-    for (int bit = 63; bit >= 0; bit--) {
-      if (started) acc = fr_sqr(acc);
-      if ((e[w] >> bit) & 1) {
-        if (started) acc = fr_mul(acc, a); else { acc = a; started = true; }
-      }
-    }
-  return acc;
+// fr.Element.Inverse; Inverse(0) = 0.  Binary extended Euclid on the raw limbs (about 500
+// shift / subtract steps on 4 words instead of ~400 Montgomery products): for the Montgomery
+// representation A = a*R it yields A^-1 = a^-1 * R^-1, and one product with R^3 gives a^-1 * R.
+inline bool fr_raw_geq(const uint64_t* a, const uint64_t* b) {
+  for (int i = 3; i >= 0; i--) {
+    if (a[i] > b[i]) return true;
+    if (a[i] < b[i]) return false;
+  }
+  return true;
 }
-// fr.BatchInvert: zeros stay zero
+inline void fr_raw_sub(uint64_t* a, const uint64_t* b) {  // a -= b (a >= b)
+  uint64_t bw = 0;
+  for (int i = 0; i < 4; i++) {
+    u128 t = (u128)a[i] - b[i] - bw;
+    a[i] = (uint64_t)t;
+    bw = (uint64_t)(t >> 64) & 1;
+  }
+}
+inline void fr_raw_half_mod(uint64_t* x) {  // x = x / 2 mod r  (x < r)
+  uint64_t c = 0;
+  if (x[0] & 1) {
+    for (int i = 0; i < 4; i++) {
+      u128 t = (u128)x[i] + FR_MOD[i] + c;
+      x[i] = (uint64_t)t;
+      c = (uint64_t)(t >> 64);
+    }
+  }
+  for (int i = 0; i < 3; i++) x[i] = (x[i] >> 1) | (x[i + 1] << 63);
+  x[3] = (x[3] >> 1) | (c << 63);
+}
+inline void fr_raw_shr1(uint64_t* x) {
+  for (int i = 0; i < 3; i++) x[i] = (x[i] >> 1) | (x[i + 1] << 63);
+  x[3] >>= 1;
+}
+inline void fr_raw_sub_mod(uint64_t* a, const uint64_t* b) {  // a = a - b mod r  (a, b < r)
+  if (fr_raw_geq(a, b)) {
+    fr_raw_sub(a, b);
+  } else {
+    uint64_t t[4] = {FR_MOD[0], FR_MOD[1], FR_MOD[2], FR_MOD[3]};
+    fr_raw_sub(t, b);  // r - b
+    uint64_t c = 0;
+    for (int i = 0; i < 4; i++) {
+      u128 s = (u128)a[i] + t[i] + c;
+      a[i] = (uint64_t)s;
+      c = (uint64_t)(s >> 64);
+    }
+  }
+}
+inline Fr fr_inv(const Fr& a) {
+  if (fr_is_zero(a)) return FR_ZERO;
+  static const Fr R3 = fr_mul(FR_R2, FR_R2);  // R^2 * R^2 * R^-1
+  uint64_t u[4] = {a.l[0], a.l[1], a.l[2], a.l[3]};
+  uint64_t v[4] = {FR_MOD[0], FR_MOD[1], FR_MOD[2], FR_MOD[3]};
+  uint64_t x1[4] = {1, 0, 0, 0}, x2[4] = {0, 0, 0, 0};
+  auto is_one = [](const uint64_t* w) { return w[0] == 1 && (w[1] | w[2] | w[3]) == 0; };
+  while (!is_one(u) && !is_one(v)) {
+    while (!(u[0] & 1)) { fr_raw_shr1(u); fr_raw_half_mod(x1); }
+    while (!(v[0] & 1)) { fr_raw_shr1(v); fr_raw_half_mod(x2); }
+    if (fr_raw_geq(u, v)) { fr_raw_sub(u, v); fr_raw_sub_mod(x1, x2); }
+    else { fr_raw_sub(v, u); fr_raw_sub_mod(x2, x1); }
+  }
+  const uint64_t* x = is_one(u) ? x1 : x2;
+  Fr raw = {{x[0], x[1], x[2], x[3]}};
+  return fr_mul(raw, R3);
+}
+// fr.BatchInvert (Montgomery's trick: one inversion, 3 products per element); zeros stay zero
 inline std::vector<Fr> fr_batch_inv(const std::vector<Fr>& v) {
-  std::vector<Fr> out(v.size());
-  for (size_t i = 0; i < v.size(); i++) out[i] = fr_inv(v[i]);
+  const size_t n = v.size();
+  std::vector<Fr> out(n);
+  Fr acc = FR_ONE;
+  for (size_t i = 0; i < n; i++) {
+    out[i] = acc;
+    if (!fr_is_zero(v[i])) acc = fr_mul(acc, v[i]);
+  }
+  acc = fr_inv(acc);
+  for (size_t i = n; i-- > 0;) {
+    if (fr_is_zero(v[i])) { out[i] = FR_ZERO; continue; }
+    Fr t = fr_mul(acc, out[i]);
+    acc = fr_mul(acc, v[i]);
+    out[i] = t;
+  }
   return out;
 }
 // common.IPA (common/util.go:26-35)

@@ -29,3 +29,9 @@ def test_merlin_kat_and_fr(pkg):
         assert out.raw.hex() == "d5a21972d0d5fe320c0d263fac7fffb8145aa640af6e9bca177c03c7efcf0615"
         want = b.fr_inv((a * x + a - x) % R) * pow(a, 5, R) % R
         assert fr_dec(fr_out.raw) == want
+    # edge values of the inversion (b = 0 makes the inverted value a itself)
+    for a in (1, 2, 3, R - 1, R - 2, (R + 1) // 2, (R - 1) // 2, 2**255 % R, 2**128, 2**64 - 1):
+        out = C.create_string_buffer(32)
+        fr_out = C.create_string_buffer(32)
+        assert lib.cdl_host_selftest(out, fr_enc(a), fr_enc(0), fr_out) == 0
+        assert fr_dec(fr_out.raw) == pow(a, -1, R) * pow(a, 5, R) % R
