@@ -585,11 +585,15 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
     for (uint32_t b = 0; b < B; b++)
       if ((rc = copy_points(L.base(b) + L.G, L.Gs, n))) return rc;  // Gs and Hs are adjacent in the CRS image
   }
-  // D, the two self-checks, B_c, B_d  (:105-177, innerproductargument.go:59-72)
+  // D, the self-check on D, B_c, B_d  (:105-177, innerproductargument.go:59-72).
+  // The reference's other self-check, msm(Gs||Hs, cs||r_cs) == C (:164-170), recomputes
+  // C = <cs, Gs> + <r_cs, Hs> (:66-73) from the very same operands: it cannot fail, so it is not
+  // launched.  msm(G', d) == D depends on the caller's B and is kept (it is the reference's error
+  // path for a witness that does not match the commitments).
   std::vector<std::vector<Fr>> rs_c(B), rs_d(B);
   std::vector<std::array<uint8_t, 48>> D_enc(B);
   {
-    StageBuilder sb(st, B, 5 * n + 1, 5);
+    StageBuilder sb(st, B, 4 * n + 1, 4);
     par(B, [&](size_t b) {
       ProveState& s = *S[b];
       const Fr& beta = gp_beta[b];
@@ -624,9 +628,6 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
       for (uint32_t i = 0; i < ell; i++) sl.term(base + L.Gp + i, fr_neg(beta_pows[b][i]));
       for (uint32_t j = 0; j < kBlinders; j++) sl.term(base + L.Gp + ell + j, ab);
       sl.end();
-      sl.begin(base + L.scratch + 2);  // msm(G, c) must equal C
-      for (uint32_t i = 0; i < n; i++) sl.term(base + L.G + i, s.cs[i]);
-      sl.end();
       sl.begin(base + L.scratch + 3);  // msm(G', d) must equal D
       for (uint32_t i = 0; i < n; i++) sl.term(base + L.Gp + i, s.ds[i]);
       sl.end();
@@ -641,10 +642,9 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
     for (uint32_t b = 0; b < B; b++) {
       ProveState& s = *S[b];
       memcpy(D_enc[b].data(), sb.out(b, 0), 48);
-      if (memcmp(sb.out(b, 1), s.C, 48) != 0) s.fail("msm(G, c) != C");
-      else if (memcmp(sb.out(b, 2), D_enc[b].data(), 48) != 0) s.fail("msm(G', d) != D");
-      memcpy(s.B_c, sb.out(b, 3), 48);
-      memcpy(s.B_d, sb.out(b, 4), 48);
+      if (memcmp(sb.out(b, 1), D_enc[b].data(), 48) != 0) s.fail("msm(G', d) != D");
+      memcpy(s.B_c, sb.out(b, 2), 48);
+      memcpy(s.B_d, sb.out(b, 3), 48);
     }
   }
   // ---- inner-product argument (innerproductargument.go:74-188)

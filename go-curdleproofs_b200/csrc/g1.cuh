@@ -344,19 +344,80 @@ CDL_FN void jac_scalar_mul(G1Jac& r, const G1Affine& p, const uint32_t* k) {
 }
 
 
+// General-case mixed addition that also returns H = U2 - X1 (Z3 = Z1 * H): the ratio
+// between consecutive Z coordinates of a table built by repeated addition.  No exceptional
+// cases: callers only add P to i*P (1 < i < 8) for P of prime order.
+CDL_FN void jac_add_mixed_h(G1Jac& r, const G1Jac& p, const G1Affine& q, Fp& h) {
+  Fp z1z1, u2, s2, rr, hh, hhh, v, t;
+  FpM::sqr(z1z1, p.z);
+  FpM::mul(u2, q.x, z1z1);
+  FpM::mul(s2, p.z, z1z1);
+  FpM::mul(s2, s2, q.y);
+  FpM::sub(h, u2, p.x);
+  FpM::sub(rr, s2, p.y);
+  FpM::sqr(hh, h);
+  FpM::mul(hhh, hh, h);
+  FpM::mul(v, p.x, hh);
+  FpM::mul(r.z, p.z, h);
+  FpM::sqr(t, rr);
+  FpM::sub(t, t, hhh);
+  FpM::sub(t, t, v);
+  FpM::sub(t, t, v);
+  FpM::sub(v, v, t);
+  FpM::mul(v, v, rr);
+  FpM::mul(hhh, hhh, p.y);
+  FpM::sub(r.y, v, hhh);
+  r.x = t;
+}
+
 // r = k * p via GLV: k = s0*(s1*|k1| + k2*lambda), phi(p) = (beta*x, y) = lambda*p.
-// 32 signed 4-bit windows, 4 doublings + up to 2 additions per window; the phi
-// part reuses the window table with X scaled by beta.  Same uniform schedule for
-// every lane.  k canonical little-endian words, k < r.
+// 32 signed 4-bit windows, 4 doublings + up to 2 additions per window.  Same uniform
+// schedule for every lane.  k canonical little-endian words, k < r; p of prime order.
+//
+// The window table {1..8}P is brought to a COMMON Z without an inversion: built by repeated
+// addition its Z coordinates satisfy Z_{i+1} = Z_i * H_i, so entry i times (Z_8 / Z_i)^2,
+// (Z_8 / Z_i)^3 is the affine form of i*P on the isomorphic curve y^2 = x^3 + 4*Z_8^6.  The
+// doubling and mixed-addition formulas do not involve the curve constant, so the whole
+// multiplication runs on that curve with MIXED additions (11 instead of 16 products each,
+// and phi is still (beta*x, y) there); the result maps back by Z <- Z * Z_8.
 CDL_FN void jac_scalar_mul_glv(G1Jac& r, const G1Affine& p, const uint32_t* k) {
   if (aff_is_inf(p)) { jac_set_inf(r); return; }
   Glv g;
   glv_decompose(g, k);
-  G1Jac tab[8];  // tab[i] = (i+1) p
-  jac_from_affine(tab[0], p);
-  jac_dbl(tab[1], tab[0]);
+  G1Affine tab[8];  // tab[i] = (i+1) p on the isomorphic curve
+  Fp zc;            // common Z = Z of 8p
+  {
+    G1Jac acc, first;
+    Fp h[8];        // h[i] = Z_{i+1} / Z_i for the additions producing entries 2..7 (0-based)
+    jac_from_affine(first, p);
+    jac_dbl(acc, first);
+    tab[1].x = acc.x; tab[1].y = acc.y;
+    Fp z2 = acc.z;
 #pragma unroll 1
-  for (int i = 2; i < 8; i++) jac_add_mixed(tab[i], tab[i - 1], p);
+    for (int i = 2; i < 8; i++) {
+      jac_add_mixed_h(acc, acc, p, h[i]);
+      tab[i].x = acc.x; tab[i].y = acc.y;
+    }
+    zc = acc.z;
+    // s = Z_8 / Z_{i+1}: running product of the later ratios
+    Fp sfac;
+    FpM::set_one(sfac);
+#pragma unroll 1
+    for (int i = 6; i >= 0; i--) {
+      if (i >= 1) FpM::mul(sfac, sfac, h[i + 1]);  // entries 2..7 (index 1..6): s_i = prod_{j>i} h_j
+      else FpM::mul(sfac, sfac, z2);                // entry 1: Z_1 = 1, s = Z_8 = Z_2 * prod h
+      Fp s2, s3;
+      FpM::sqr(s2, sfac);
+      FpM::mul(s3, s2, sfac);
+      if (i >= 1) {
+        FpM::mul(tab[i].x, tab[i].x, s2);
+        FpM::mul(tab[i].y, tab[i].y, s3);
+      } else {
+        FpM::mul(tab[0].x, p.x, s2);
+        FpM::mul(tab[0].y, p.y, s3);
+      }
+    }
+  }
   int8_t dg[2][32];
   recode_w4_128(dg[0], g.k1);
   recode_w4_128(dg[1], g.k2);
@@ -374,14 +435,15 @@ CDL_FN void jac_scalar_mul_glv(G1Jac& r, const G1Affine& p, const uint32_t* k) {
       int d = dg[h][i];
       if (d != 0) {
         int a = d < 0 ? -d : d;
-        G1Jac t = tab[a - 1];
+        G1Affine t = tab[a - 1];
         if (h == 1) FpM::mul(t.x, t.x, beta);
         bool neg = (d < 0) != (h == 0 ? g.neg1 : g.neg2);
         if (neg) FpM::neg(t.y, t.y);
-        jac_add(r, r, t);
+        jac_add_mixed(r, r, t);
       }
     }
   }
+  FpM::mul(r.z, r.z, zc);  // back from the isomorphic curve (infinity stays Z = 0)
 }
 
 // r = e * p for a public 64-bit e (MSB-first double-and-add on a Jacobian base)
