@@ -49,15 +49,18 @@ __device__ __forceinline__ T ld_stream16(const T* p) {
   return v;
 }
 
-struct alignas(8) MsmRec {
+struct alignas(16) MsmRec {
   uint32_t k1p[4];
   uint32_t k2p[4];
   uint32_t pidx;   // pool index of the base
   uint32_t flags;  // bit 0: negate the P part, bit 1: negate the phi(P) part
+  uint32_t pad[2];
+  Fp bx;           // beta * x of the base: the x coordinate of phi(P), computed once per term here
+                   // instead of once per term by all 32 lanes of the bucket warp
 };
 
-__global__ void k_msm_recode(const uint32_t* __restrict__ idx, const Fr* __restrict__ scalars,
-                             MsmRec* __restrict__ rec, int nterm) {
+__global__ void k_msm_recode(const G1Affine* __restrict__ points, const uint32_t* __restrict__ idx,
+                             const Fr* __restrict__ scalars, MsmRec* __restrict__ rec, int nterm) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nterm) return;
   Fr km = scalars[t], k;
@@ -70,6 +73,10 @@ __global__ void k_msm_recode(const uint32_t* __restrict__ idx, const Fr* __restr
   r.pidx = idx[t] & 0x7fffffffu;
   bool flip = (idx[t] >> 31) != 0;
   r.flags = ((g.neg1 != flip) ? 1u : 0u) | ((g.neg2 != flip) ? 2u : 0u);
+  r.pad[0] = r.pad[1] = 0;
+  Fp beta, x = points[r.pidx].x;
+  fp_set_beta(beta);
+  FpM::mul(r.bx, x, beta);
   rec[t] = r;
 }
 
@@ -85,15 +92,12 @@ k_msm_warp(const G1Affine* __restrict__ points, const MsmRec* __restrict__ rec, 
   const MsmSub s = subs[sub];
   G1Xyzz bk[8];
   uint32_t nonempty = 0;
-  Fp beta;
-  fp_set_beta(beta);
 #pragma unroll 1
   for (uint32_t t = 0; t < s.term_cnt; t++) {
-    const MsmRec r = ld_stream8(rec + s.term_off + t);
+    const MsmRec r = ld_stream16(rec + s.term_off + t);
     G1Affine p = ld_stream16(points + r.pidx);
     if (aff_is_inf(p)) continue;  // uniform across the warp
-    Fp bx;
-    FpM::mul(bx, p.x, beta);
+    const Fp& bx = r.bx;
 #pragma unroll 1
     for (int h = 0; h < 2; h++) {
       int d = glv_digit(h == 0 ? r.k1p : r.k2p, w);
@@ -168,15 +172,12 @@ k_msm_warp_smem(const G1Affine* __restrict__ points, const MsmRec* __restrict__ 
   const int w = threadIdx.x;
   const MsmSub s = subs[sub];
   uint32_t nonempty = 0;
-  Fp beta;
-  fp_set_beta(beta);
 #pragma unroll 1
   for (uint32_t t = 0; t < s.term_cnt; t++) {
     const MsmRec r = rec[s.term_off + t];
     G1Affine p = points[r.pidx];
     if (aff_is_inf(p)) continue;  // uniform across the warp
-    Fp bx;
-    FpM::mul(bx, p.x, beta);
+    const Fp& bx = r.bx;
 #pragma unroll 1
     for (int h = 0; h < 2; h++) {
       int d = glv_digit(h == 0 ? r.k1p : r.k2p, w);
@@ -294,7 +295,7 @@ void launch_msm_tp(const G1Affine* points, const uint32_t* idx, const Fr* scalar
   size_t win_bytes = ((size_t)nsub * kTpWindows * sizeof(G1Jac) + 255) & ~(size_t)255;
   G1Jac* win = (G1Jac*)((uint8_t*)scratch + rec_bytes);
   G1Jac* wsum = (G1Jac*)((uint8_t*)scratch + rec_bytes + win_bytes);
-  if (nterm > 0) k_msm_recode<<<(nterm + 127) / 128, 128, 0, st>>>(idx, scalars, rec, nterm);
+  if (nterm > 0) k_msm_recode<<<(nterm + 127) / 128, 128, 0, st>>>(points, idx, scalars, rec, nterm);
   static const int variant = [] {
     const char* e = getenv("CDL_MSM_WARP");
     return !e ? 0 : e[0] == 'j' ? 1 : e[0] == 'x' ? 2 : 0;
