@@ -101,6 +101,7 @@ void cdl_destroy(cdl_ctx* c) {
   cudaEventDestroy(c->ev0);
   cudaEventDestroy(c->ev1);
   if (c->base_ev) cudaEventDestroy(c->base_ev);
+  if (c->ev_sync) cudaEventDestroy(c->ev_sync);
   cudaStreamDestroy(c->stream);
   delete c;
 }

@@ -16,6 +16,16 @@ struct cdl_ctx {
   std::string name;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev_sync = nullptr;  // cudaEventBlockingSync: waiting host threads sleep instead of spinning
+  // Wait for everything queued on the stream.  Lanes and ranks share the host cores with the
+  // Fiat-Shamir work, so a waiting thread must not burn one (cudaStreamSynchronize spins).
+  cudaError_t sync_stream() {
+    if (!ev_sync && cudaEventCreateWithFlags(&ev_sync, cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess)
+      return cudaStreamSynchronize(stream);
+    cudaError_t e = cudaEventRecord(ev_sync, stream);
+    if (e != cudaSuccess) return e;
+    return cudaEventSynchronize(ev_sync);
+  }
   std::mutex mu;
   std::string err;
   void* engine = nullptr;  // cdlh::Engine, created on first protocol-level call

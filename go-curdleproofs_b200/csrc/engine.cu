@@ -140,7 +140,7 @@ int32_t Engine::load_crs(const Layout& L, const cdl_crs* crs) {
 int32_t Engine::upload_points(uint32_t dst, const void* host_affine, size_t count) {
   if (!count) return CDL_OK;
   CDL_CUDA(ctx_, cudaMemcpyAsync(d_pool_ + dst, host_affine, count * sizeof(G1Affine), cudaMemcpyHostToDevice, ctx_->stream));
-  CDL_CUDA(ctx_, cudaStreamSynchronize(ctx_->stream));  // caller memory is pageable and may go away
+  CDL_CUDA(ctx_, ctx_->sync_stream());  // caller memory is pageable and may go away
   return CDL_OK;
 }
 
@@ -154,7 +154,7 @@ int32_t Engine::upload_jac(uint32_t dst, const void* host_jac, size_t count) {
   cdl::launch_jac_to_affine((const cdl::G1Jac*)s_jac_.d, d_pool_ + dst, (int)count, ctx_->stream);
   tock(3, 0, 240.0 * count);
   CDL_CUDA(ctx_, cudaGetLastError());
-  CDL_CUDA(ctx_, cudaStreamSynchronize(ctx_->stream));
+  CDL_CUDA(ctx_, ctx_->sync_stream());
   finish_timing();
   return CDL_OK;
 }
@@ -162,7 +162,7 @@ int32_t Engine::upload_jac(uint32_t dst, const void* host_jac, size_t count) {
 int32_t Engine::download_points(uint32_t src, void* host_affine, size_t count) {
   if (!count) return CDL_OK;
   CDL_CUDA(ctx_, cudaMemcpyAsync(host_affine, d_pool_ + src, count * sizeof(G1Affine), cudaMemcpyDeviceToHost, ctx_->stream));
-  CDL_CUDA(ctx_, cudaStreamSynchronize(ctx_->stream));
+  CDL_CUDA(ctx_, ctx_->sync_stream());
   return CDL_OK;
 }
 
@@ -201,7 +201,7 @@ int32_t Engine::compress(const std::vector<uint32_t>& src, std::vector<uint8_t>&
   tock(3, 3.0 * n, 148.0 * n);
   CDL_CUDA(ctx_, cudaGetLastError());
   CDL_CUDA(ctx_, cudaMemcpyAsync(s_out_.h, s_out_.d, n * 48, cudaMemcpyDeviceToHost, ctx_->stream));
-  CDL_CUDA(ctx_, cudaStreamSynchronize(ctx_->stream));
+  CDL_CUDA(ctx_, ctx_->sync_stream());
   finish_timing();
   memcpy(out48.data(), s_out_.h, n * 48);
   return CDL_OK;
@@ -224,7 +224,7 @@ int32_t Engine::decompress(const uint8_t* enc48, const std::vector<uint32_t>& ds
   tock(2, (480.0 + 3193.0) * n, 148.0 * n);
   CDL_CUDA(ctx_, cudaGetLastError());
   CDL_CUDA(ctx_, cudaMemcpyAsync(s_st_.h, s_st_.d, n, cudaMemcpyDeviceToHost, ctx_->stream));
-  CDL_CUDA(ctx_, cudaStreamSynchronize(ctx_->stream));
+  CDL_CUDA(ctx_, ctx_->sync_stream());
   finish_timing();
   memcpy(status.data(), s_st_.h, n);
   return CDL_OK;
@@ -288,7 +288,7 @@ int32_t Engine::run_msm(MsmStage& st) {
   }
   CDL_CUDA(ctx_, cudaGetLastError());
   CDL_CUDA(ctx_, cudaMemcpyAsync(s_out_.h, s_out_.d, nt * 48, cudaMemcpyDeviceToHost, ctx_->stream));
-  CDL_CUDA(ctx_, cudaStreamSynchronize(ctx_->stream));
+  CDL_CUDA(ctx_, ctx_->sync_stream());
   finish_timing();
   memcpy(st.out48.data(), s_out_.h, nt * 48);
   return CDL_OK;
@@ -308,7 +308,7 @@ int32_t Engine::run_elem(const std::vector<ElemOp>& ops, const std::vector<Fr>& 
   cdl::launch_elem_ops(d_pool_, (const ElemOp*)s_ops_.d, (const cdl::Fr*)s_sc_.d, (int)n, ctx_->stream);
   tock(1, 3193.0 * n, 288.0 * n);  // §8d: 3193 modmul per scalar multiplication; src + add + dst points
   CDL_CUDA(ctx_, cudaGetLastError());
-  CDL_CUDA(ctx_, cudaStreamSynchronize(ctx_->stream));
+  CDL_CUDA(ctx_, ctx_->sync_stream());
   finish_timing();
   return CDL_OK;
 }
