@@ -45,7 +45,7 @@ struct MsmSub {
 struct MsmTask2 {
   uint32_t sub_off, sub_cnt, out_idx, pad;
 };
-constexpr uint32_t kMsmChunk = 256;  // longest chunk; msm_tp_pick_chunk shortens it for small launches
+constexpr uint32_t kMsmChunk = 128;  // terms per bucket warp (msm_tp_pick_chunk)
 size_t msm_tp_scratch_bytes(size_t nterm, size_t nsub, size_t ntasks);
 uint32_t msm_tp_pick_chunk(size_t nterm, int sm_count);
 void launch_msm_tp(const G1Affine* points, const uint32_t* idx, const Fr* scalars, int nterm, const MsmSub* subs,
