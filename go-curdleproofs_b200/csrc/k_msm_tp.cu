@@ -3,6 +3,8 @@
 //   k_msm_recode  thread per term : fr.Element (Montgomery) -> canonical -> GLV split
 //                                   k = s0*(s1*|k1| + k2*lambda), both < 2^127, stored in
 //                                   biased form so that a window digit is one nibble - 8
+//   k_msm_warp_gmem (default) / k_msm_warp / k_msm_warp_smem<>: the same walk with the buckets in
+//                 an L2-resident global scratch / in local memory / in shared memory (see below)
 //   k_msm_warp    warp per (chunk of a) task, lane = one of the 32 signed 4-bit windows:
 //                 every lane walks the chunk's terms serially and adds +-P / +-phi(P) into
 //                 its 8 private XYZZ buckets (local memory), then reduces them with the
@@ -15,7 +17,9 @@
 //                 windows top-down (4 doublings + 1 addition), normalises, stores the affine
 //                 point and its 48-byte encoding.  The 124-doubling chain is serial per MSM
 //                 but runs at full lane efficiency across thousands of MSMs.
+#include <algorithm>
 #include <cstdlib>
+#include <mutex>
 
 #define CDL_FP_MUL_CALL 1
 #include "codec.cuh"
@@ -142,6 +146,129 @@ k_msm_warp(const G1Affine* __restrict__ points, const MsmRec* __restrict__ rec, 
 // sm[(a*36 + i)*32 + l], so every access is bank-conflict free whatever bucket each lane picks.
 // The private-array form above keeps the buckets in local memory, whose 49 KB per warp thrash
 // L1/L2 and show up as DRAM traffic hundreds of times the algorithmic bytes.
+// Same walk with the buckets in an explicitly managed GLOBAL scratch: one 49 KB region per
+// resident warp slot (SM x CTA slot x warp), claimed from a per-SM bitmap when the CTA starts and
+// released when it ends, so that every CTA that ever runs on an SM reuses the same addresses and
+// the whole working set (resident warps x 49 KB = 58 MB) stays in L2 with ordinary write-back
+// caching.  uint4 granules, layout [bucket][granule][lane]: a warp access is 512 contiguous bytes.
+constexpr int kSlotsPerSm = 4;
+constexpr int kMaxSmIds = 192;
+constexpr size_t kWarpBucketBytes = 8 * sizeof(G1Xyzz) * 32;
+
+__global__ void __launch_bounds__(128, 2)
+k_msm_warp_gmem(const G1Affine* __restrict__ points, const MsmRec* __restrict__ rec, const MsmSub* __restrict__ subs,
+                int nsub, G1Jac* __restrict__ win, uint4* __restrict__ scratch, uint32_t* __restrict__ bitmap) {
+  __shared__ uint32_t slot_sh;
+  uint32_t smid;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+  if (smid >= (uint32_t)kMaxSmIds) __trap();
+  if (threadIdx.x == 0) {
+    uint32_t k = 0;
+    for (uint32_t tries = 0;; tries++) {
+      uint32_t old = atomicOr(&bitmap[smid], 1u << k);
+      if (!((old >> k) & 1u)) break;
+      k = (k + 1) % kSlotsPerSm;
+      if (tries > (1u << 28)) __trap();  // a leaked slot must surface as an error, never as a hang
+    }
+    slot_sh = k;
+  }
+  __syncthreads();
+  const uint32_t slot = slot_sh;
+  const int sub = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int w = threadIdx.x & 31;
+  // slot-major: the two slots normally in use on every SM form one contiguous prefix of the buffer
+  uint4* bk = scratch + (((size_t)slot * kMaxSmIds + smid) * 4 + (threadIdx.x >> 5)) * (kWarpBucketBytes / 16) + w;
+  if (sub < nsub) {
+    const MsmSub s = subs[sub];
+    uint32_t nonempty = 0;
+#pragma unroll 1
+    for (uint32_t t = 0; t < s.term_cnt; t++) {
+      const MsmRec r = ld_stream16(rec + s.term_off + t);
+      G1Affine p = ld_stream16(points + r.pidx);
+      if (aff_is_inf(p)) continue;  // uniform across the warp
+      const Fp& bx = r.bx;
+#pragma unroll 1
+      for (int h = 0; h < 2; h++) {
+        int d = glv_digit(h == 0 ? r.k1p : r.k2p, w);
+        if (d == 0) continue;
+        bool neg = (d < 0) != (((r.flags >> h) & 1u) != 0);
+        int a = (d < 0 ? -d : d) - 1;
+        G1Affine q;
+        q.x = h == 0 ? p.x : bx;
+        q.y = p.y;
+        if (neg) FpM::neg(q.y, q.y);
+        uint4* slotp = bk + (size_t)a * 12 * 32;
+        G1Xyzz b;
+        uint4* bw = reinterpret_cast<uint4*>(&b);
+        if (!((nonempty >> a) & 1u)) {
+          xyzz_from_affine(b, q);
+          nonempty |= 1u << a;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 12; i++) bw[i] = slotp[i * 32];
+          xyzz_add_mixed(b, b, q);
+        }
+#pragma unroll
+        for (int i = 0; i < 12; i++) slotp[i * 32] = bw[i];
+      }
+    }
+    G1Xyzz run, acc;
+    xyzz_set_inf(run);
+    xyzz_set_inf(acc);
+#pragma unroll 1
+    for (int a = nonempty ? 31 - __clz(nonempty) : -1; a >= 0; a--) {
+      if ((nonempty >> a) & 1u) {
+        G1Xyzz b;
+        uint4* bw = reinterpret_cast<uint4*>(&b);
+        const uint4* slotp = bk + (size_t)a * 12 * 32;
+#pragma unroll
+        for (int i = 0; i < 12; i++) bw[i] = slotp[i * 32];
+        xyzz_add(run, run, b);
+      }
+      xyzz_add(acc, acc, run);
+    }
+    G1Jac j;
+    xyzz_to_jac(j, acc);
+    win[(size_t)w * nsub + sub] = j;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) atomicAnd(&bitmap[smid], ~(1u << slot));
+}
+
+// device-wide scratch of the gmem variant, shared by every context / lane on the device
+struct GmemScratch {
+  uint4* buf = nullptr;
+  uint32_t* bitmap = nullptr;
+  size_t hot_bytes = 0;  // prefix normally in use (2 CTA slots per SM)
+  bool persist = false;  // an L2 persisting carve-out was granted
+};
+static GmemScratch* gmem_scratch() {
+  static GmemScratch per_dev[64];
+  static std::mutex mu;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(mu);
+  GmemScratch& g = per_dev[dev & 63];
+  if (!g.buf) {
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms > kMaxSmIds) return nullptr;
+    size_t bytes = (size_t)kMaxSmIds * kSlotsPerSm * 4 * kWarpBucketBytes;  // %smid may skip disabled units
+    if (cudaMalloc(&g.buf, bytes) != cudaSuccess) { g.buf = nullptr; return nullptr; }
+    if (cudaMalloc(&g.bitmap, 4096) != cudaSuccess) { cudaFree(g.buf); g.buf = nullptr; return nullptr; }
+    cudaMemset(g.bitmap, 0, 4096);
+    g.hot_bytes = (size_t)2 * kMaxSmIds * 4 * kWarpBucketBytes;
+    // keep the bucket scratch resident in L2: persisting carve-out + access-policy window (set per stream)
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess && prop.persistingL2CacheMaxSize > 0 && !getenv("CDL_NO_L2_PERSIST")) {
+      size_t want = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, g.hot_bytes);
+      g.persist = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess;
+    }
+    cudaGetLastError();
+  }
+  return &g;
+}
+
 template <class Bucket>
 struct SmemBucketOps;
 template <>
@@ -298,7 +425,7 @@ void launch_msm_tp(const G1Affine* points, const uint32_t* idx, const Fr* scalar
   if (nterm > 0) k_msm_recode<<<(nterm + 127) / 128, 128, 0, st>>>(points, idx, scalars, rec, nterm);
   static const int variant = [] {
     const char* e = getenv("CDL_MSM_WARP");
-    return !e ? 0 : e[0] == 'j' ? 1 : e[0] == 'x' ? 2 : 0;
+    return !e ? 3 : e[0] == 'j' ? 1 : e[0] == 'x' ? 2 : e[0] == 'l' ? 0 : 3;  // default: global scratch
   }();
   if (nsub > 0) {
     if (variant == 1) {
@@ -308,6 +435,27 @@ void launch_msm_tp(const G1Affine* points, const uint32_t* idx, const Fr* scalar
                                                            (int)(8 * sizeof(G1Xyzz) * 32));
       (void)attr;
       k_msm_warp_smem<G1Xyzz><<<nsub, 32, 8 * sizeof(G1Xyzz) * 32, st>>>(points, rec, subs, nsub, win);
+    } else if (variant == 3) {
+      GmemScratch* g = gmem_scratch();
+      if (!g) {  // scratch allocation failed: private (local-memory) buckets
+        k_msm_warp<<<(nsub + 3) / 4, 128, 0, st>>>(points, rec, subs, nsub, win);
+      } else {
+        if (g->persist) {
+          cudaDeviceProp prop;
+          int dev = 0;
+          cudaGetDevice(&dev);
+          static int max_window = [&] { int v = 0; cudaDeviceGetAttribute(&v, cudaDevAttrMaxAccessPolicyWindowSize, dev); return v; }();
+          cudaStreamAttrValue av = {};
+          av.accessPolicyWindow.base_ptr = g->buf;
+          av.accessPolicyWindow.num_bytes = std::min<size_t>(g->hot_bytes, (size_t)max_window);
+          av.accessPolicyWindow.hitRatio = 1.0f;
+          av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+          av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+          cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
+          (void)prop;
+        }
+        k_msm_warp_gmem<<<(nsub + 3) / 4, 128, 0, st>>>(points, rec, subs, nsub, win, g->buf, g->bitmap);
+      }
     } else {
       k_msm_warp<<<(nsub + 3) / 4, 128, 0, st>>>(points, rec, subs, nsub, win);
     }
