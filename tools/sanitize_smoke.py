@@ -1,0 +1,32 @@
+#!/usr/bin/env python
+"""Small end-to-end workload for `compute-sanitizer --tool memcheck`: a 3 000-term large MSM (every
+kernel of the Pippenger chain, including a degenerate all-equal-scalar input for the slice path) and
+a 100-instance Whisk round trip on ell = 12 (throughput MSM chain with the bucket scratch, lanes)."""
+import importlib
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+pkg = importlib.import_module("go-curdleproofs_b200")
+from oracle import bls12381 as b  # noqa: E402
+from util import aff_enc, fr_enc  # noqa: E402
+
+ctx = pkg.Context(0)
+n = 3000
+r = pkg.Rand(5)
+pts = ctx.g1_scalar_mul_affine(aff_enc(b.G1_GEN) * n, r.get_frs(n), broadcast=False)
+out1 = ctx.g1_msm(pts, pkg.Rand(6).get_frs(n))
+out2 = ctx.g1_msm(pts, fr_enc(123456789) * n)
+ell, B = 12, 100
+crs = ctx.generate_crs(ell, pkg.Rand(0))
+rr = pkg.Rand(1000)
+rG = ctx.g1_scalar_mul_affine(aff_enc(b.G1_GEN) * ell, rr.get_frs(ell), broadcast=False)
+krG = ctx.g1_scalar_mul_affine(rG, rr.get_frs(ell), broadcast=False)
+e1, e2 = ctx.g1_compress(rG), ctx.g1_compress(krG)
+pre = b"".join(e1[48 * j:48 * j + 48] + e2[48 * j:48 * j + 48] for j in range(ell)) * B
+post, proofs, status = ctx.whisk_generate_shuffle_proof_batch(crs, pre, [pkg.Rand(3000 + i) for i in range(B)])
+ok, st = ctx.whisk_is_valid_shuffle_proof_batch(crs, pre, post, proofs, [pkg.Rand(2000 + i) for i in range(B)])
+assert status == [0] * B and ok == [1] * B and st == [0] * B
+print("sanitize smoke ok")
