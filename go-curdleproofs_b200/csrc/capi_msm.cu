@@ -5,7 +5,17 @@
 // one partial sum per rank.  NCCL is bound at run time (dlopen), so the library
 // loads on hosts without it.
 #include <dlfcn.h>
+#if __has_include(<nccl.h>)
 #include <nccl.h>
+#else
+// the five entry points used below, declared locally (NCCL's ABI: 128-byte unique id, opaque
+// communicator, ncclChar = 0, ncclSuccess = 0); the library itself is bound with dlopen
+#include <cuda_runtime.h>
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef enum { ncclSuccess = 0 } ncclResult_t;
+typedef enum { ncclChar = 0 } ncclDataType_t;
+#endif
 
 #include <cstdlib>
 #include <cstring>

@@ -560,7 +560,7 @@ cudaError_t launch_big_msm(const G1Affine* points, const Fr* scalars, const BigM
   k_big_slice<<<sm_count * 4, kBigCtaThreads, 0, st>>>(points, phi, (uint32_t)d.n, entries, meta, slices, slice_out);
   k_big_large_finish<<<sm_count, kBigCtaThreads, 0, st>>>(meta, large, slice_out, buckets);
   // bucket reduction
-  int Lc = d.M < 16 ? d.M : 16;
+  int Lc = d.M < 8 ? d.M : 8;  // buckets per reduce1 thread: shorter serial chain, more threads
   int per = d.M / Lc;
   int total = d.nlocal * per;
   k_big_reduce1<<<(total + 127) / 128, 128, 0, st>>>(buckets, d.M, Lc, total, red[0]);
