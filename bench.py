@@ -231,9 +231,37 @@ def msm_sweep(ctx, pkg, log2_sizes, reps, world, rank, peak_modmul, barrier):
         out.append({"log2n": lg, "ms": best, "mpoints_per_s": n / best / 1e3, "gmodmul_per_s": mm / best / 1e6,
                     "frac_of_int_peak": mm / (best * 1e-3) / (peak_modmul * world), "check": "ok" if ok else "MISMATCH",
                     "windows_per_rank": pkg.comm_partition(n, world, rank)[3]})
+    cpu = None
+    if rank == 0 and not os.environ.get("CDL_BENCH_NO_CPU_MSM"):
+        # the same MSM on the host cores with the CPU oracle port (bucket method, windows spread over
+        # threads; the reference's gnark-crypto MultiExp cannot be built here), bounded to 2^16 terms
+        try:
+            from oracle.cbackend import CBackend
+            from util import RP_INV, P as FP_P
+
+            lg = min(16, min(log2_sizes))
+            n = 1 << lg
+            raw_p = dp.download(96 * n)
+            raw_s = ds.download(32 * n)
+            cp = b"".join((int.from_bytes(raw_p[48 * i:48 * i + 48], "little") * RP_INV % FP_P).to_bytes(48, "little")
+                          for i in range(2 * n))
+            cs = b"".join((int.from_bytes(raw_s[32 * i:32 * i + 32], "little") * RR_INV % R).to_bytes(32, "little")
+                          for i in range(n))
+            cb = CBackend(accelerate_keccak=False)
+            cores = os.cpu_count() or 1
+            t0 = time.perf_counter()
+            res_cpu = cb.msm_raw(cp, cs, n, cores)
+            dt = time.perf_counter() - t0
+            gpu_res, _ = ctx.g1_msm_sharded_device(dp, ds, n)
+            same = all((int.from_bytes(gpu_res[48 * k:48 * k + 48], "little") * RP_INV % FP_P) ==
+                       int.from_bytes(res_cpu[48 * k:48 * k + 48], "little") for k in range(2))
+            cpu = {"log2n": lg, "ms": dt * 1e3, "mpoints_per_s": n / dt / 1e6, "cores": cores, "kind": "port",
+                   "check": "equal to the GPU result" if same else "MISMATCH"}
+        except Exception as e:  # reported baseline, never required
+            cpu = {"failed": str(e)}
     for d in (dp, da, ds):
         d.close()
-    return out
+    return out, cpu
 
 
 def gpu_main(args):
@@ -345,9 +373,9 @@ def gpu_main(args):
                    "value": world * B * 2 / float(tv[0]), "unit": "verifications/s", "batch_per_gpu": B,
                    "timing": "wall clock through the C ABI with host buffers, 2 batches after 1 warm-up",
                    "verdicts": "as expected" if verdict_ok else "MISMATCH"}
-    msm = None
+    msm, msm_cpu = None, None
     if not args.no_msm:
-        msm = msm_sweep(ctx, pkg, [16, 20, 22] if not args.msm_sizes else [int(x) for x in args.msm_sizes.split(",")],
+        msm, msm_cpu = msm_sweep(ctx, pkg, [16, 20, 22] if not args.msm_sizes else [int(x) for x in args.msm_sizes.split(",")],
                         2, world, rank, peak_modmul, barrier)
 
     t = torch.tensor([wall, busy_ms / 1e3], dtype=torch.float64, device=f"cuda:{local}")
@@ -422,7 +450,7 @@ def gpu_main(args):
         if msm is not None:
             line["msm"] = {"workload": "standalone G1 MSM, random points/scalars, device resident"
                                        + (f", windows dealt to {world} ranks + NCCL all-gather" if world > 1 else ""),
-                           "sizes": msm}
+                           "sizes": msm, "cpu_baseline": msm_cpu}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 from oracle.cbackend import build as build_oracle
