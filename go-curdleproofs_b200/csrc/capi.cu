@@ -134,7 +134,6 @@ int32_t cdl_g1_msm_batch(cdl_ctx* c, const cdl_g1_affine* points, const cdl_fr* 
     tasks[j].pad = 0;
     if (tasks[j].term_cnt > max_terms) max_terms = tasks[j].term_cnt;
   }
-  if (max_terms > kMsmMaxTerms && (int)k < kMsmSplitThreshold) return c->fail(CDL_ERR_TOO_LARGE, "msm: %zu terms exceed the small-MSM limit %zu", max_terms, (size_t)kMsmMaxTerms);
   G1Affine* d_pts = (G1Affine*)c->buf(0, (total + 1) * sizeof(G1Affine));
   Fr* d_sc = (Fr*)c->buf(1, (total + 1) * sizeof(Fr));
   uint32_t* d_idx = (uint32_t*)c->buf(2, (total + 1) * sizeof(uint32_t));
@@ -147,7 +146,7 @@ int32_t cdl_g1_msm_batch(cdl_ctx* c, const cdl_g1_affine* points, const cdl_fr* 
     k_iota<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(d_idx, (uint32_t)total);
   }
   CDL_CUDA(c, cudaMemcpyAsync(d_tasks, tasks.data(), k * sizeof(MsmTask), cudaMemcpyHostToDevice, c->stream));
-  if ((int)k >= kMsmSplitThreshold) {
+  if ((int)k >= kMsmSplitThreshold || max_terms > kMsmSplitTerms) {
     std::vector<MsmSub> subs;
     std::vector<MsmTask2> tasks2;
     msm_build_subs(tasks.data(), k, msm_tp_pick_chunk(total, c->sm_count), subs, tasks2);

@@ -252,7 +252,7 @@ int32_t Engine::run_msm(MsmStage& st) {
   CDL_CUDA(ctx_, cudaMemcpyAsync(s_task_.d, s_task_.h, nt * sizeof(MsmTask), cudaMemcpyHostToDevice, ctx_->stream));
   double alg = 0;
   for (auto& t : st.tasks) alg += msm_algorithmic_modmul(t.term_cnt);
-  if ((int)nt >= cdl::kMsmSplitThreshold) {
+  if ((int)nt >= cdl::kMsmSplitThreshold || max_terms > cdl::kMsmSplitTerms) {
     // throughput path: recode + warp-per-chunk + per-task combine
     std::vector<cdl::MsmSub> subs;
     std::vector<cdl::MsmTask2> tasks2;

@@ -4,11 +4,11 @@
 // terms; SURVEY.md §8a rows a1,a3-a6,a8,a10-a15), many MSMs per launch (the 4/6
 // MSMs of an IPA / SameMSM round, times the number of proofs in a batch).
 //
-// Signed 4-bit windows, W = 64 windows x 8 buckets = 512 threads.  Phases:
-//   1. recode   : scalars Montgomery -> canonical, k -> min(k, r-k) with the
-//                 point negated, k' = k + 0x0888..8 so that window digits are
+// GLV halves, signed 4-bit windows, W = 32 windows x 8 buckets = 256 threads.  Phases:
+//   1. recode   : scalars Montgomery -> canonical -> k = +-|k1| +- k2*lambda, both
+//                 halves biased by 0x0888..8 so that window digits are
 //                 ((k' >> 4w) & 15) - 8 with no carry chain at lookup time;
-//                 k' (32 B/term) is staged in shared memory.
+//                 the two biased halves (32 B/term) are staged in shared memory.
 //   2. accumulate: thread (w, d) walks the terms, adds every point whose digit
 //                 in window w is +-d into its private XYZZ bucket (mixed add).
 //                 Lanes search for their next term independently (cheap) and
@@ -17,7 +17,7 @@
 //   3. reduce   : sum_d d*B_d per window as suffix scan + butterfly over the 8
 //                 lanes of a window with warp shuffles (6 adds instead of 16).
 //   4. combine  : binary tree over windows, level L doubles the upper operand
-//                 4*2^L times (252 doublings on the critical path, 6 adds).
+//                 4*2^L times (124 doublings on the critical path, 5 adds).
 //   5. normalise: one inversion, affine result (+ optional compressed bytes).
 #define CDL_FP_MUL_CALL 1  // one shared product body: the hot loops fit the instruction caches (mont.cuh)
 #include "codec.cuh"
@@ -27,42 +27,8 @@ namespace cdl {
 
 constexpr int kMsmC = 4;
 constexpr int kMsmBuckets = 8;     // 2^(c-1)
-constexpr int kMsmWindows = 64;    // 63 signed windows (bits 0..251) + top raw window
+constexpr int kMsmWindows = 32;    // signed 4-bit windows of the 127-bit GLV halves
 constexpr int kMsmThreads = kMsmBuckets * kMsmWindows;
-
-// 0x0888...8: 2^(c-1) in each of the 63 signed windows (bits 0..251)
-__device__ __forceinline__ uint32_t msm_bias_word(int i) { return i == 7 ? 0x08888888u : 0x88888888u; }
-
-// canonical k (8 words) -> biased k' and sign.  k < r.
-__device__ __forceinline__ bool msm_recode(uint32_t* kp, const Fr& k) {
-  // neg = r - k
-  uint32_t ng[8];
-  CC cc;
-  ng[0] = sub_cc(cc, FR_MOD_D[0], k.v[0]);
-#pragma unroll
-  for (int i = 1; i < 7; i++) ng[i] = subc_cc(cc, FR_MOD_D[i], k.v[i]);
-  ng[7] = subc(cc, FR_MOD_D[7], k.v[7]);
-  // use the negative when k > r - k  <=>  (r-k) - k borrows
-  CC c2;
-  (void)sub_cc(c2, ng[0], k.v[0]);
-#pragma unroll
-  for (int i = 1; i < 8; i++) (void)subc_cc(c2, ng[i], k.v[i]);
-  bool neg = subc(c2, 0, 0) != 0;
-  uint32_t m[8];
-#pragma unroll
-  for (int i = 0; i < 8; i++) m[i] = neg ? ng[i] : k.v[i];
-  CC c3;
-  kp[0] = add_cc(c3, m[0], msm_bias_word(0));
-#pragma unroll
-  for (int i = 1; i < 7; i++) kp[i] = addc_cc(c3, m[i], msm_bias_word(i));
-  kp[7] = addc(c3, m[7], msm_bias_word(7));
-  return neg;
-}
-
-__device__ __forceinline__ int msm_digit(const uint32_t* kp, int w) {
-  int nib = (int)((kp[w >> 3] >> ((w & 7) * 4)) & 15u);
-  return w == kMsmWindows - 1 ? nib : nib - 8;
-}
 
 __device__ __forceinline__ void xyzz_shfl_down(G1Xyzz& r, const G1Xyzz& p, int delta, int width) {
   const uint32_t* s = reinterpret_cast<const uint32_t*>(&p);
@@ -78,41 +44,52 @@ __device__ __forceinline__ void msm_bucket_phases(const G1Affine* __restrict__ p
                                                   uint8_t* smem_raw, G1Xyzz& acc) {
   const int T = (int)task.term_cnt;
   const int tid = threadIdx.x;
-  // layout: kp[T][8] words, then pidx[T] words
+  // layout: kp[T][8] words (biased |k1|, biased k2), then pidx[T] words (bit 31 / 30: negate P / phi(P))
   uint32_t* kp = reinterpret_cast<uint32_t*>(smem_raw);
   uint32_t* pidx = kp + (size_t)T * 8;
 
-  // ---- phase 1: recode
+  // ---- phase 1: recode.  k = +-|k1| +- k2*lambda (GLV, both halves < 2^127), biased so that a
+  // signed window digit is one nibble - 8 (glv.cuh): half the windows and half the doublings of
+  // the final combine compared with windows over the 255-bit scalar.
   for (int t = tid; t < T; t += kMsmThreads) {
     Fr km = scalars[task.term_off + t], k;
     FrM::from_mont(k, km);
-    uint32_t tmp[8];
-    bool neg = msm_recode(tmp, k);
+    Glv g;
+    glv_decompose(g, k.v);
+    uint32_t b1[4], b2[4];
+    glv_bias(b1, g.k1);
+    glv_bias(b2, g.k2);
 #pragma unroll
-    for (int i = 0; i < 8; i++) kp[t * 8 + i] = tmp[i];
-    pidx[t] = idx[task.term_off + t] ^ (neg ? 0x80000000u : 0u);
+    for (int i = 0; i < 4; i++) { kp[t * 8 + i] = b1[i]; kp[t * 8 + 4 + i] = b2[i]; }
+    uint32_t raw = idx[task.term_off + t];
+    bool flip = (raw >> 31) != 0;
+    pidx[t] = (raw & 0x3fffffffu) | ((g.neg1 != flip) ? 0x80000000u : 0u) | ((g.neg2 != flip) ? 0x40000000u : 0u);
   }
   __syncthreads();
 
-  // ---- phase 2: bucket accumulation
+  // ---- phase 2: bucket accumulation over the 2T (term, half) pairs
   const int w = tid >> 3;
   const int mybucket = (tid & 7) + 1;
   xyzz_set_inf(acc);
-  int t = 0;
+  Fp beta;
+  fp_set_beta(beta);
+  int t = 0;  // index into the 2T pairs: pair = 2*term + half
   while (true) {
     int found = -1;
     int sgn = 0;
-    while (t < T) {
-      int d = msm_digit(kp + t * 8, w);
+    while (t < 2 * T) {
+      int d = glv_digit(kp + (t >> 1) * 8 + (t & 1) * 4, w);
       int a = d < 0 ? -d : d;
       if (a == mybucket) { found = t; sgn = d; t++; break; }
       t++;
     }
     if (!__any_sync(0xffffffffu, found >= 0)) break;
     if (found >= 0) {
-      uint32_t pi = pidx[found];
-      G1Affine q = points[pi & 0x7fffffffu];
-      bool neg = ((pi >> 31) != 0) != (sgn < 0);
+      uint32_t pi = pidx[found >> 1];
+      G1Affine q = points[pi & 0x3fffffffu];
+      const int h = found & 1;
+      if (h) FpM::mul(q.x, q.x, beta);
+      bool neg = (((pi >> (31 - h)) & 1u) != 0) != (sgn < 0);
       if (neg) FpM::neg(q.y, q.y);
       xyzz_add_mixed(acc, acc, q);
     }

@@ -404,14 +404,16 @@ size_t msm_tp_scratch_bytes(size_t nterm, size_t nsub, size_t ntasks) {
 // 128: 378, 160: 374, 256: 384, 512: 404, 1 024: 427; batched verification alone (one 712-term MSM
 // per proof) gains 5-12 % from 64-128 over 256.  CDL_MSM_CHUNK overrides the default of 128.
 uint32_t msm_tp_pick_chunk(size_t nterm, int sm_count) {
-  (void)nterm;
-  (void)sm_count;
   static const uint32_t forced = [] {
     const char* e = getenv("CDL_MSM_CHUNK");
     int v = e ? atoi(e) : 0;
     return (uint32_t)(v >= 8 && v <= 4096 ? v : 0);
   }();
-  return forced ? forced : kMsmChunk;
+  if (forced) return forced;
+  // latency regime (a handful of large MSMs, e.g. the verifier's 5*ell + 8 terms for one proof):
+  // too few 128-term chunks to occupy the machine, so cut finer and shorten each warp's serial walk
+  if (nterm / kMsmChunk < (size_t)2 * sm_count) return 32;
+  return kMsmChunk;
 }
 
 void launch_msm_tp(const G1Affine* points, const uint32_t* idx, const Fr* scalars, int nterm, const MsmSub* subs,

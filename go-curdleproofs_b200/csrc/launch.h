@@ -73,6 +73,8 @@ cudaError_t launch_exclusive_scan(uint32_t* counts, uint32_t n, uint32_t* bsum, 
 // Latency path (k_msm.cu): one CTA per task.  Callers switch to the throughput path at
 // kMsmSplitThreshold tasks per launch.
 constexpr int kMsmSplitThreshold = 96;
+// ... or when one task is long enough that a single CTA's thread-per-bucket walk is the slower choice
+constexpr size_t kMsmSplitTerms = 384;
 void launch_msm_small(const G1Affine* points, const uint32_t* idx, const Fr* scalars, const MsmTask* tasks,
                       int ntasks, size_t max_terms, G1Affine* out_aff, uint8_t* out_c48, cudaStream_t st);
 

@@ -15,7 +15,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 def main():
     pkg = importlib.import_module("go-curdleproofs_b200")
     ctx = pkg.Context(0)
-    for ell in (60, 124, 508):
+    ells = [int(x) for x in sys.argv[1:]] or [60, 124, 508]
+    for ell in ells:
         r = pkg.Rand(0)
         crs = ctx.generate_crs(ell, r)
         k = r.get_fr()
