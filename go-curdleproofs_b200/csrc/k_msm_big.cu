@@ -515,6 +515,7 @@ size_t big_msm_scratch_bytes(const BigMsmDims& d) { return big_layout(d).total; 
 // All launches go to `st`; nothing synchronises.  d_out receives one G1Jac.
 cudaError_t launch_big_msm(const G1Affine* points, const Fr* scalars, const BigMsmDims& d, int normalize,
                            void* scratch, int sm_count, G1Jac* d_out, cudaStream_t st) {
+  msm_l2_carveout(false);  // the point gathers want the whole L2
   uint8_t* base = (uint8_t*)scratch;
   BigLayout L = big_layout(d);
   uint32_t* counts = (uint32_t*)(base + L.counts);

@@ -239,16 +239,30 @@ k_msm_warp_gmem(const G1Affine* __restrict__ points, const MsmRec* __restrict__ 
 struct GmemScratch {
   uint4* buf = nullptr;
   uint32_t* bitmap = nullptr;
-  size_t hot_bytes = 0;  // prefix normally in use (2 CTA slots per SM)
-  bool persist = false;  // an L2 persisting carve-out was granted
+  size_t hot_bytes = 0;     // prefix normally in use (2 CTA slots per SM)
+  size_t persist_bytes = 0; // size of the L2 persisting carve-out this path asks for (0: unsupported)
+  bool persist = false;     // the carve-out is currently set
 };
-static GmemScratch* gmem_scratch() {
-  static GmemScratch per_dev[64];
-  static std::mutex mu;
+static std::mutex g_scratch_mu;
+static GmemScratch g_scratch[64];
+
+// The persisting carve-out takes L2 away from everything else on the device, so it is only held
+// while batched-MSM launches are being issued: the large-MSM path (whose point gathers want the
+// whole L2) releases it, the next batched launch takes it back.
+void msm_l2_carveout(bool on) {
   int dev = 0;
   cudaGetDevice(&dev);
-  std::lock_guard<std::mutex> lk(mu);
-  GmemScratch& g = per_dev[dev & 63];
+  std::lock_guard<std::mutex> lk(g_scratch_mu);
+  GmemScratch& g = g_scratch[dev & 63];
+  if (!g.persist_bytes || g.persist == on) return;
+  if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, on ? g.persist_bytes : 0) == cudaSuccess) g.persist = on;
+  cudaGetLastError();
+}
+static GmemScratch* gmem_scratch() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(g_scratch_mu);
+  GmemScratch& g = g_scratch[dev & 63];
   if (!g.buf) {
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -261,8 +275,7 @@ static GmemScratch* gmem_scratch() {
     // keep the bucket scratch resident in L2: persisting carve-out + access-policy window (set per stream)
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess && prop.persistingL2CacheMaxSize > 0 && !getenv("CDL_NO_L2_PERSIST")) {
-      size_t want = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, g.hot_bytes);
-      g.persist = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess;
+      g.persist_bytes = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, g.hot_bytes);
     }
     cudaGetLastError();
   }
@@ -442,7 +455,8 @@ void launch_msm_tp(const G1Affine* points, const uint32_t* idx, const Fr* scalar
       if (!g) {  // scratch allocation failed: private (local-memory) buckets
         k_msm_warp<<<(nsub + 3) / 4, 128, 0, st>>>(points, rec, subs, nsub, win);
       } else {
-        if (g->persist) {
+        if (g->persist_bytes) {
+          msm_l2_carveout(true);
           cudaDeviceProp prop;
           int dev = 0;
           cudaGetDevice(&dev);

@@ -48,6 +48,7 @@ struct MsmTask2 {
 constexpr uint32_t kMsmChunk = 128;  // terms per bucket warp (msm_tp_pick_chunk)
 size_t msm_tp_scratch_bytes(size_t nterm, size_t nsub, size_t ntasks);
 uint32_t msm_tp_pick_chunk(size_t nterm, int sm_count);
+void msm_l2_carveout(bool on);  // persisting-L2 window of the bucket scratch: held by the batched path only
 void launch_msm_tp(const G1Affine* points, const uint32_t* idx, const Fr* scalars, int nterm, const MsmSub* subs,
                    int nsub, const MsmTask2* tasks, int ntasks, G1Affine* out_aff, uint8_t* out_c48, void* scratch,
                    cudaStream_t st);
