@@ -87,6 +87,8 @@ def load_library():
     lib.cdl_whisk_is_valid_shuffle_proof.argtypes = [vp, vp, vp, vp, sz, sz, vp, sz, vp, i32p]
     lib.cdl_whisk_generate_shuffle_proof_batch.argtypes = [vp, vp, sz, vp, C.POINTER(vp), vp, vp, sz, i32p]
     lib.cdl_whisk_is_valid_shuffle_proof_batch.argtypes = [vp, vp, sz, vp, vp, vp, sz, C.POINTER(vp), i32p, i32p]
+    lib.cdl_whisk_generate_tracker_proof_batch.argtypes = [vp, sz, vp, vp, C.POINTER(vp), vp, i32p]
+    lib.cdl_whisk_is_valid_tracker_proof_batch.argtypes = [vp, sz, vp, vp, vp, i32p, i32p]
     lib.cdl_host_selftest.argtypes = [vp, vp, vp, vp]
     lib.cdl_engine_stats.argtypes = [vp, vp, vp, vp, vp, C.c_int]
     lib.cdl_engine_busy_ms.argtypes = [vp, C.POINTER(C.c_double)]
@@ -471,6 +473,25 @@ def _ctx_whisk_is_valid_batch(self, crs: CRS, pre: bytes, post: bytes, proofs: b
     return list(ok), list(status)
 
 
+def _ctx_whisk_generate_tracker_proof_batch(self, trackers: bytes, ks: bytes, rands):
+    """whisk.GenerateWhiskTrackerProof for B trackers -> (B x 128 proof bytes, status list)."""
+    B = len(rands)
+    proofs = C.create_string_buffer(B * 128)
+    status = (C.c_int32 * B)()
+    rh = (C.c_void_p * B)(*[r.h for r in rands])
+    self._chk(self.lib.cdl_whisk_generate_tracker_proof_batch(self.h, B, trackers, ks, rh, proofs, status))
+    return proofs.raw, list(status)
+
+
+def _ctx_whisk_is_valid_tracker_proof_batch(self, trackers: bytes, k_comms: bytes, proofs: bytes):
+    """whisk.IsValidWhiskTrackerProof for B trackers -> (ok list, status list)."""
+    B = len(trackers) // 96
+    ok = (C.c_int32 * B)()
+    status = (C.c_int32 * B)()
+    self._chk(self.lib.cdl_whisk_is_valid_tracker_proof_batch(self.h, B, trackers, k_comms, proofs, ok, status))
+    return list(ok), list(status)
+
+
 def _ctx_engine_stats(self, reset: bool = False):
     """Per kernel class (msm, elem, decompress, compress): launches, event ms, algorithmic modmul / bytes."""
     n = (C.c_uint64 * 4)()
@@ -515,6 +536,8 @@ Context.whisk_generate_shuffle_proof = _ctx_whisk_generate
 Context.whisk_is_valid_shuffle_proof = _ctx_whisk_is_valid
 Context.whisk_generate_shuffle_proof_batch = _ctx_whisk_generate_batch
 Context.whisk_is_valid_shuffle_proof_batch = _ctx_whisk_is_valid_batch
+Context.whisk_generate_tracker_proof_batch = _ctx_whisk_generate_tracker_proof_batch
+Context.whisk_is_valid_tracker_proof_batch = _ctx_whisk_is_valid_tracker_proof_batch
 Context.launch_count = _ctx_launch_count
 Context.engine_busy_ms = _ctx_engine_busy_ms
 Context.set_lanes = _ctx_set_lanes

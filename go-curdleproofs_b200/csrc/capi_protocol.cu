@@ -602,4 +602,126 @@ int32_t cdl_whisk_is_valid_shuffle_proof(cdl_ctx* c, const cdl_crs* crs, const u
   return status;
 }
 
+
+// ------------------------------------------------------------------ Whisk tracker opening proofs
+// whisk.GenerateWhiskTrackerProof / IsValidWhiskTrackerProof (whisk/whisk.go:116-176): a Schnorr-style
+// proof that the tracker (rG, krG) and the commitment kG share k.  Constant work per tracker (3 / 4
+// scalar multiplications), so it is only worth a launch when batched over validators; the layout in
+// the point pool is [G | per instance: rG krG kG A B A' B'].
+namespace {
+constexpr uint32_t kTpStride = 7;
+const uint8_t kGenEnc[48] = {0x97, 0xf1, 0xd3, 0xa7, 0x31, 0x97, 0xd7, 0x94, 0x26, 0x95, 0x63, 0x8c, 0x4f, 0xa9, 0xac, 0x0f,
+                             0xc3, 0x68, 0x8c, 0x4f, 0x97, 0x74, 0xb9, 0x05, 0xa1, 0x4e, 0x3a, 0x3f, 0x17, 0x1b, 0xac, 0x58,
+                             0x6c, 0x55, 0xe8, 0x3f, 0xf9, 0x7a, 0x1a, 0xef, 0xfb, 0x3a, 0xf0, 0x0a, 0xdb, 0x22, 0xc6, 0xbb};
+
+cdlh::Fr tracker_challenge(const uint8_t* kG, const uint8_t* krG, const uint8_t* rG, const uint8_t* A, const uint8_t* B) {
+  cdlh::Transcript tr("whisk_opening_proof");
+  tr.append_points("tracker_opening_proof", kG, 1);
+  tr.append_points("tracker_opening_proof", kGenEnc, 1);
+  tr.append_points("tracker_opening_proof", krG, 1);
+  tr.append_points("tracker_opening_proof", rG, 1);
+  tr.append_points("tracker_opening_proof", A, 1);
+  tr.append_points("tracker_opening_proof", B, 1);
+  return tr.challenge("tracker_opening_proof_challenge");
+}
+}  // namespace
+
+int32_t cdl_whisk_generate_tracker_proof_batch(cdl_ctx* c, size_t B, const uint8_t* trackers, const cdl_fr* ks,
+                                               cdl_rand* const* rands, uint8_t* proofs, int32_t* status_out) {
+  if (!c || !trackers || !ks || !rands || !proofs || !status_out || B == 0 || B > (1u << 24)) return CDL_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(c->mu);
+  CDL_CUDA(c, cudaSetDevice(c->device));
+  Engine* E = engine_of(c);
+  int32_t rc;
+  if ((rc = E->ensure_pool(1 + B * kTpStride)) || (rc = put_generator(E, 0))) return rc;
+  // tracker.getPoints(): rG, krG with curve + subgroup checks
+  std::vector<uint32_t> dst(2 * B);
+  for (size_t b = 0; b < B; b++) { dst[2 * b] = (uint32_t)(1 + b * kTpStride); dst[2 * b + 1] = dst[2 * b] + 1; }
+  std::vector<uint8_t> st;
+  if ((rc = E->decompress(trackers, dst, st))) return rc;
+  // kG = k*G, A = blinder*G, B = blinder*rG
+  std::vector<Fr> sc(2 * B);
+  std::vector<cdl::ElemOp> ops(3 * B);
+  for (size_t b = 0; b < B; b++) {
+    status_out[b] = (st[2 * b] || st[2 * b + 1]) ? CDL_ERR_DECODE : CDL_OK;
+    uint32_t base = (uint32_t)(1 + b * kTpStride);
+    memcpy(&sc[2 * b], &ks[b], 32);
+    sc[2 * b + 1] = rands[b]->r.get_fr();  // blinder (whisk.go:157)
+    ops[3 * b] = cdl::ElemOp{0, cdl::kNoPoint, base + 2, (uint32_t)(2 * b)};
+    ops[3 * b + 1] = cdl::ElemOp{0, cdl::kNoPoint, base + 3, (uint32_t)(2 * b + 1)};
+    ops[3 * b + 2] = cdl::ElemOp{base, cdl::kNoPoint, base + 4, (uint32_t)(2 * b + 1)};
+  }
+  if ((rc = E->run_elem(ops, sc))) return rc;
+  std::vector<uint32_t> src(3 * B);
+  for (size_t b = 0; b < B; b++)
+    for (uint32_t j = 0; j < 3; j++) src[3 * b + j] = (uint32_t)(1 + b * kTpStride + 2 + j);
+  std::vector<uint8_t> enc;
+  if ((rc = E->compress(src, enc))) return rc;
+  E->threads().parallel_for(B, [&](size_t b) {
+    uint8_t* out = proofs + 128 * b;
+    if (status_out[b] != CDL_OK) { memset(out, 0, 128); return; }
+    const uint8_t* kG = enc.data() + 48 * (3 * b);
+    const uint8_t* A = kG + 48;
+    const uint8_t* Bp = kG + 96;
+    const uint8_t* rG = trackers + 96 * b;
+    Fr ch = tracker_challenge(kG, rG + 48, rG, A, Bp);
+    Fr s = cdlh::fr_sub(sc[2 * b + 1], cdlh::fr_mul(ch, sc[2 * b]));  // s = blinder - challenge*k
+    memcpy(out, A, 48);
+    memcpy(out + 48, Bp, 48);
+    cdlh::fr_to_bytes_be(out + 96, s);
+  });
+  return CDL_OK;
+}
+
+int32_t cdl_whisk_is_valid_tracker_proof_batch(cdl_ctx* c, size_t B, const uint8_t* trackers, const uint8_t* k_comms,
+                                               const uint8_t* proofs, int32_t* ok, int32_t* status_out) {
+  if (!c || !trackers || !k_comms || !proofs || !ok || !status_out || B == 0 || B > (1u << 24)) return CDL_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(c->mu);
+  CDL_CUDA(c, cudaSetDevice(c->device));
+  Engine* E = engine_of(c);
+  int32_t rc;
+  if ((rc = E->ensure_pool(1 + B * kTpStride)) || (rc = put_generator(E, 0))) return rc;
+  // decode: proof (A, B, s), tracker (rG, krG), commitment kG
+  std::vector<uint8_t> enc(B * 5 * 48);
+  std::vector<uint32_t> dst(5 * B);
+  std::vector<Fr> S(B);
+  for (size_t b = 0; b < B; b++) {
+    uint32_t base = (uint32_t)(1 + b * kTpStride);
+    uint8_t* e = enc.data() + b * 5 * 48;
+    memcpy(e, trackers + 96 * b, 96);          // rG, krG
+    memcpy(e + 96, k_comms + 48 * b, 48);      // kG
+    memcpy(e + 144, proofs + 128 * b, 96);     // A, B
+    for (uint32_t j = 0; j < 5; j++) dst[5 * b + j] = base + j;
+    status_out[b] = cdlh::fr_from_bytes_be_canonical(S[b], proofs + 128 * b + 96) ? CDL_OK : CDL_ERR_DECODE;
+  }
+  std::vector<uint8_t> st;
+  if ((rc = E->decompress(enc.data(), dst, st))) return rc;
+  cdlh::MsmStage stage;
+  stage.idx.resize(4 * B);
+  stage.sc.resize(4 * B);
+  stage.tasks.resize(2 * B);
+  E->threads().parallel_for(B, [&](size_t b) {
+    for (uint32_t j = 0; j < 5; j++)
+      if (st[5 * b + j]) status_out[b] = CDL_ERR_DECODE;
+    uint32_t base = (uint32_t)(1 + b * kTpStride);
+    const uint8_t* e = enc.data() + b * 5 * 48;
+    Fr ch = status_out[b] == CDL_OK ? tracker_challenge(e + 96, e + 48, e, e + 144, e + 192) : cdlh::FR_ZERO;
+    // A' = s*G + c*kG ; B' = s*rG + c*krG
+    stage.idx[4 * b] = 0;            stage.sc[4 * b] = S[b];
+    stage.idx[4 * b + 1] = base + 2; stage.sc[4 * b + 1] = ch;
+    stage.idx[4 * b + 2] = base;     stage.sc[4 * b + 2] = S[b];
+    stage.idx[4 * b + 3] = base + 1; stage.sc[4 * b + 3] = ch;
+    stage.tasks[2 * b] = cdl::MsmTask{(uint32_t)(4 * b), 2, base + 5, 0};
+    stage.tasks[2 * b + 1] = cdl::MsmTask{(uint32_t)(4 * b + 2), 2, base + 6, 0};
+  });
+  if ((rc = E->run_msm(stage))) return rc;
+  for (size_t b = 0; b < B; b++) {
+    const uint8_t* e = enc.data() + b * 5 * 48;
+    bool good = status_out[b] == CDL_OK && memcmp(stage.out48.data() + 48 * (2 * b), e + 144, 48) == 0 &&
+                memcmp(stage.out48.data() + 48 * (2 * b + 1), e + 192, 48) == 0;
+    ok[b] = good ? 1 : 0;
+  }
+  return CDL_OK;
+}
+
 }  // extern "C"

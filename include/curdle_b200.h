@@ -183,6 +183,17 @@ int32_t cdl_whisk_is_valid_shuffle_proof_batch(cdl_ctx* ctx, const cdl_crs* crs,
                                                const uint8_t* pre_trackers, const uint8_t* post_trackers,
                                                const uint8_t* proofs, size_t proof_len, cdl_rand* const* rands,
                                                int32_t* ok, int32_t* status);
+/* whisk.GenerateWhiskTrackerProof (whisk/whisk.go:149-176), batched over B validators: tracker b is
+ * 96 bytes {rG, krG}, ks[b] the secret, one blinder is drawn from rands[b]; proofs receives B x 128
+ * bytes (A | B | s, whisk/types.go:98-127).  status[b] = CDL_ERR_DECODE when the tracker does not decode. */
+#define CDL_WHISK_TRACKER_PROOF_SIZE 128
+int32_t cdl_whisk_generate_tracker_proof_batch(cdl_ctx* ctx, size_t B, const uint8_t* trackers, const cdl_fr* ks,
+                                               cdl_rand* const* rands, uint8_t* proofs, int32_t* status);
+/* whisk.IsValidWhiskTrackerProof (whisk/whisk.go:116-147): k_comms holds B x 48 bytes (kG).
+ * ok[b] is the reference's bool, status[b] its error (CDL_ERR_DECODE for malformed proof / points). */
+int32_t cdl_whisk_is_valid_tracker_proof_batch(cdl_ctx* ctx, size_t B, const uint8_t* trackers, const uint8_t* k_comms,
+                                               const uint8_t* proofs, int32_t* ok, int32_t* status);
+
 /* Host-side self test (no GPU needed): out32 receives Merlin's published
  * "test protocol" challenge computed by the library's transcript code;
  * fr_out receives (a*b + a - b)^-1 * a^5 computed by the host Fr code. */
