@@ -101,6 +101,7 @@ def load_library():
     lib.cdl_dev_upload.argtypes = [vp, vp, vp, sz]
     lib.cdl_dev_download.argtypes = [vp, vp, vp, sz]
     lib.cdl_g1_scalar_mul_affine_device.argtypes = [vp, vp, vp, sz, sz, vp]
+    lib.cdl_g1_fold_device.argtypes = [vp, vp, vp, vp, sz]
     lib.cdl_g1_msm_device.argtypes = [vp, vp, vp, sz, C.c_uint32, C.c_uint32, i32, vp, f32p]
     lib.cdl_set_msm_window.argtypes = [vp, i32]
     lib.cdl_comm_unique_id.argtypes = [vp]
@@ -277,6 +278,10 @@ def _ctx_dev_buffer(self, nbytes: int) -> DeviceBuffer:
 def _ctx_g1_scalar_mul_affine_device(self, d_in: DeviceBuffer, d_s: DeviceBuffer, n: int, broadcast: bool,
                                      d_out: DeviceBuffer):
     self._chk(self.lib.cdl_g1_scalar_mul_affine_device(self.h, d_in.ptr, d_s.ptr, n, 0 if broadcast else 1, d_out.ptr))
+
+
+def _ctx_g1_fold_device(self, d_L: DeviceBuffer, d_R: DeviceBuffer, d_x: DeviceBuffer, n: int):
+    self._chk(self.lib.cdl_g1_fold_device(self.h, d_L.ptr, d_R.ptr, d_x.ptr, n))
 
 
 def _ctx_g1_msm_device(self, d_points, d_scalars, n: int, part_index: int = 0, part_count: int = 1,
@@ -520,6 +525,7 @@ def _ctx_launch_count(self) -> int:
 Context.int_peak_cfg = _ctx_int_peak_cfg
 Context.dev_buffer = _ctx_dev_buffer
 Context.g1_scalar_mul_affine_device = _ctx_g1_scalar_mul_affine_device
+Context.g1_fold_device = _ctx_g1_fold_device
 Context.g1_msm_device = _ctx_g1_msm_device
 Context.set_msm_window = _ctx_set_msm_window
 Context.comm_init = _ctx_comm_init

@@ -161,6 +161,18 @@ int32_t cdl_g1_scalar_mul_affine_device(cdl_ctx* c, const cdl_g1_affine* d_in, c
   return CDL_OK;
 }
 
+// L[i] += x * R[i] on device vectors (innerproductargument.go:155-166 with the bases resident in HBM)
+int32_t cdl_g1_fold_device(cdl_ctx* c, cdl_g1_affine* d_L, const cdl_g1_affine* d_R, const cdl_fr* d_x, size_t n) {
+  if (!c || (n && (!d_L || !d_R || !d_x)) || n >= ((size_t)1 << 31)) return CDL_ERR_INVALID_ARG;
+  if (!n) return CDL_OK;
+  std::lock_guard<std::mutex> lk(c->mu);
+  CDL_CUDA(c, cudaSetDevice(c->device));
+  launch_scalar_mul((const G1Affine*)d_R, (const Fr*)d_x, 0, (const G1Affine*)d_L, (G1Affine*)d_L, (int)n, c->stream);
+  CDL_CUDA(c, cudaGetLastError());
+  CDL_CUDA(c, cudaStreamSynchronize(c->stream));
+  return CDL_OK;
+}
+
 int32_t cdl_g1_msm_device(cdl_ctx* c, const cdl_g1_affine* d_points, const cdl_fr* d_scalars, size_t n,
                           uint32_t part_index, uint32_t part_count, int32_t normalize, cdl_g1_jac* d_out,
                           float* kernel_ms) {

@@ -237,6 +237,10 @@ int32_t cdl_dev_download(cdl_ctx* ctx, void* h_dst, const void* d_src, size_t by
 int32_t cdl_g1_scalar_mul_affine_device(cdl_ctx* ctx, const cdl_g1_affine* d_in, const cdl_fr* d_s, size_t n,
                                         size_t scalar_stride, cdl_g1_affine* d_out);
 
+/* Base folding L[i] += x * R[i] on device vectors (innerproductargument.go:155-166,
+ * samemultiscalarargument.go:129-135); d_x points to one fr.Element in device memory. */
+int32_t cdl_g1_fold_device(cdl_ctx* ctx, cdl_g1_affine* d_L, const cdl_g1_affine* d_R, const cdl_fr* d_x, size_t n);
+
 /* (*G1Jac).MultiExp on device vectors.  part_index / part_count select the
  * windows part_index, part_index + part_count, ... of the signed-digit
  * decomposition (0 / 1 = the whole MSM); the partial sum is returned already

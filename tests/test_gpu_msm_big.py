@@ -135,6 +135,20 @@ def test_device_scalar_mul_and_sum(ctx, sweep):
     ds.upload(frs_enc(a[:n]))
     ctx.g1_scalar_mul_affine_device(dp, ds, n, False, dp)
     assert dp.download() == pts[: 96 * n]
+    # device-resident fold L[i] += x * R[i]: (a_i + x * a_{i+1000}) * G
+    x = 0x1234567890abcdef1234567890abcdef % R
+    dl = ctx.dev_buffer(96 * 1000)
+    dr = ctx.dev_buffer(96 * 1000)
+    dx = ctx.dev_buffer(32)
+    dl.upload(pts[: 96 * 1000])
+    dr.upload(pts[96 * 1000: 96 * 2000])
+    dx.upload(fr_enc(x))
+    ctx.g1_fold_device(dl, dr, dx, 1000)
+    want = ctx.g1_scalar_mul_affine(aff_enc(b.G1_GEN) * 1000, frs_enc([(a[i] + x * a[i + 1000]) % R for i in range(1000)]),
+                                    broadcast=False)
+    assert dl.download() == want
+    for d in (dl, dr, dx):
+        d.close()
     # Gsum-style sum of many points (crs.go:41-48) goes through the same path
     from util import aff_dec
     assert aff_dec(ctx.g1_sum_affine(pts[: 96 * n])) == b.g1_mul(b.G1_GEN, sum(a[:n]) % R)
