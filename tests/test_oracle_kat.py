@@ -24,6 +24,17 @@ def test_generator_encodings():
     assert bls.g1_compress(bls.g1_mul(bls.G1_GEN, 2)).hex() == (
         "a572cbea904d67468808c8eb50a9450c9721db309128012543902d0ac358a62ae28f75bb8f1c7c42c39a8c5529bf0f4e")
     assert bls.g1_compress(None) == bytes([0xC0]) + bytes(47)
+    # ... and for sk = 3, 4, 5 (public eth2 interop / test-vector keys): scalar multiplication, the
+    # sign bit of the encoding and decompression are pinned by them
+    kat = {
+        3: "89ece308f9d1f0131765212deca99697b112d61f9be9a5f1f3780a51335b3ff981747a0b2ca2179b96d2c0c9024e5224",
+        4: "ac9b60d5afcbd5663a8a44b7c5a02f19e9a77ab0a35bd65809bb5c67ec582c897feb04decc694b13e08587f3ff9b5b60",
+        5: "b0e7791fb972fe014159aa33a98622da3cdc98ff707965e536d8636b5fcc5ac7a91a8c46e59a00dca575af0f18fb13dc",
+    }
+    for k, enc in kat.items():
+        pt = bls.g1_mul(bls.G1_GEN, k)
+        assert bls.g1_compress(pt).hex() == enc
+        assert bls.g1_decompress(bytes.fromhex(enc)) == pt
 
 
 def test_keccak_against_hashlib():
