@@ -189,3 +189,22 @@ def test_msm_batch_throughput_path(ctx, pts):
     cb = CBackend(accelerate_keccak=False)
     want = [cb.msm(ps[offs[i]:offs[i + 1]], ks[offs[i]:offs[i + 1]]) for i in range(len(sizes))]
     assert got == want
+
+
+def test_public_known_answers(ctx):
+    """Independent of the oracle: eth2 public keys for sk = 1..5 are the compressed k*G."""
+    kat = [
+        "97f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb",
+        "a572cbea904d67468808c8eb50a9450c9721db309128012543902d0ac358a62ae28f75bb8f1c7c42c39a8c5529bf0f4e",
+        "89ece308f9d1f0131765212deca99697b112d61f9be9a5f1f3780a51335b3ff981747a0b2ca2179b96d2c0c9024e5224",
+        "ac9b60d5afcbd5663a8a44b7c5a02f19e9a77ab0a35bd65809bb5c67ec582c897feb04decc694b13e08587f3ff9b5b60",
+        "b0e7791fb972fe014159aa33a98622da3cdc98ff707965e536d8636b5fcc5ac7a91a8c46e59a00dca575af0f18fb13dc",
+    ]
+    gen = aff_enc(b.G1_GEN)
+    pts = ctx.g1_scalar_mul_affine(gen * 5, frs_enc([1, 2, 3, 4, 5]), broadcast=False)
+    assert ctx.g1_compress(pts).hex() == "".join(kat)
+    dec, st = ctx.g1_decompress(bytes.fromhex("".join(kat)))
+    assert dec == pts and not any(st)
+    # 1*G + 2*G + ... as one MSM: 15*G = 5*G + 10*G
+    s15 = ctx.g1_msm(pts, frs_enc([1, 1, 1, 1, 1]))
+    assert jac_dec(s15) == jac_dec(ctx.g1_msm(gen, fr_enc(15)))
