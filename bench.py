@@ -252,7 +252,7 @@ def msm_sweep(ctx, pkg, log2_sizes, reps, world, rank, peak_modmul, barrier):
             t0 = time.perf_counter()
             res_cpu = cb.msm_raw(cp, cs, n, cores)
             dt = time.perf_counter() - t0
-            gpu_res, _ = ctx.g1_msm_sharded_device(dp, ds, n)
+            gpu_res, _ = ctx.g1_msm_device(dp, ds, n)  # local (non-collective): only rank 0 is here
             same = all((int.from_bytes(gpu_res[48 * k:48 * k + 48], "little") * RP_INV % FP_P) ==
                        int.from_bytes(res_cpu[48 * k:48 * k + 48], "little") for k in range(2))
             cpu = {"log2n": lg, "ms": dt * 1e3, "mpoints_per_s": n / dt / 1e6, "cores": cores, "kind": "port",
