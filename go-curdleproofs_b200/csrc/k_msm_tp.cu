@@ -168,7 +168,7 @@ k_msm_warp_gmem(const G1Affine* __restrict__ points, const MsmRec* __restrict__ 
       uint32_t old = atomicOr(&bitmap[smid], 1u << k);
       if (!((old >> k) & 1u)) break;
       k = (k + 1) % kSlotsPerSm;
-      if (tries > (1u << 28)) __trap();  // a leaked slot must surface as an error, never as a hang
+      if (tries > (1u << 22)) __trap();  // a leaked slot must surface as an error, never as a hang
     }
     slot_sh = k;
   }
