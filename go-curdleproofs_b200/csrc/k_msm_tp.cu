@@ -1,22 +1,25 @@
-// Throughput path for many small MSMs per launch (batched proving/verification).
+// Throughput path for many small MSMs per launch (batched proving / verification), and for a
+// few long ones (the verifier's 5*ell + 8 terms for a single proof).
 //
-//   k_msm_recode  thread per term : fr.Element (Montgomery) -> canonical -> GLV split
-//                                   k = s0*(s1*|k1| + k2*lambda), both < 2^127, stored in
-//                                   biased form so that a window digit is one nibble - 8
-//   k_msm_warp_gmem (default) / k_msm_warp / k_msm_warp_smem<>: the same walk with the buckets in
-//                 an L2-resident global scratch / in local memory / in shared memory (see below)
-//   k_msm_warp    warp per (chunk of a) task, lane = one of the 32 signed 4-bit windows:
-//                 every lane walks the chunk's terms serially and adds +-P / +-phi(P) into
-//                 its 8 private XYZZ buckets (local memory), then reduces them with the
-//                 running-sum trick.  All 32 lanes do the same amount of work on every
-//                 term (the term's point is one broadcast load), so lane efficiency is
-//                 ~15/16 regardless of the MSM size — unlike thread-per-bucket, whose
-//                 lanes idle on load imbalance when a window has few points per bucket.
+//   k_msm_recode    thread per term: fr.Element (Montgomery) -> canonical -> GLV split
+//                   k = s0*(s1*|k1| + k2*lambda), both < 2^127, stored biased so that a window
+//                   digit is one nibble - 8; beta*x of the base (the x of phi(P)) once per term
+//   k_msm_warp_gmem warp per chunk (<= 128 terms, msm_tp_pick_chunk) of a task, lane = one of the
+//                   32 signed 4-bit windows: every lane walks the chunk's terms serially and adds
+//                   +-P / +-phi(P) into its 8 XYZZ buckets, then reduces them with the running-sum
+//                   trick from the highest non-empty bucket.  All 32 lanes do the same amount of
+//                   work on every term (the term's point is one broadcast load), so lane
+//                   efficiency is ~15/16 whatever the MSM size — unlike thread-per-bucket, whose
+//                   lanes idle on load imbalance when a window has few points per bucket.
+//                   The buckets (49 KB per warp) live in a global scratch whose regions are
+//                   reused per SM slot and pinned in L2 (see k_msm_warp_gmem).
+//   k_msm_warp / k_msm_warp_smem<>: the same walk with the buckets in local memory / in shared
+//                   memory; measured alternatives, selectable with CDL_MSM_WARP=l / j / x
 //   k_msm_chunk_sum thread per (task, window): sums the chunk partials
-//   k_msm_combine thread per task : walks the
-//                 windows top-down (4 doublings + 1 addition), normalises, stores the affine
-//                 point and its 48-byte encoding.  The 124-doubling chain is serial per MSM
-//                 but runs at full lane efficiency across thousands of MSMs.
+//   k_msm_combine_tp thread per task: walks the windows top-down (4 doublings + 1 addition),
+//                   normalises, stores the affine point and its 48-byte encoding.  The 124-doubling
+//                   chain is serial per MSM but runs at full lane efficiency across thousands of
+//                   MSMs, and overlaps the other lanes' kernels in a batched call.
 #include <algorithm>
 #include <cstdlib>
 #include <mutex>
