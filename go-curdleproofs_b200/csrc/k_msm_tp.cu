@@ -155,16 +155,23 @@ k_msm_warp(const G1Affine* __restrict__ points, const MsmRec* __restrict__ rec, 
 // the whole working set (resident warps x 49 KB = 58 MB) stays in L2 with ordinary write-back
 // caching.  uint4 granules, layout [bucket][granule][lane]: a warp access is 512 contiguous bytes.
 constexpr int kSlotsPerSm = 4;
-constexpr int kMaxSmIds = 192;
+
+// %smid values are below %nsmid, which can exceed the SM count when units are fused off
+__global__ void k_query_nsmid(uint32_t* out) {
+  uint32_t n;
+  asm volatile("mov.u32 %0, %%nsmid;" : "=r"(n));
+  out[0] = n;
+}
 constexpr size_t kWarpBucketBytes = 8 * sizeof(G1Xyzz) * 32;
 
 __global__ void __launch_bounds__(128, 2)
 k_msm_warp_gmem(const G1Affine* __restrict__ points, const MsmRec* __restrict__ rec, const MsmSub* __restrict__ subs,
-                int nsub, G1Jac* __restrict__ win, uint4* __restrict__ scratch, uint32_t* __restrict__ bitmap) {
+                int nsub, G1Jac* __restrict__ win, uint4* __restrict__ scratch, uint32_t* __restrict__ bitmap,
+                uint32_t nsmid) {
   __shared__ uint32_t slot_sh;
   uint32_t smid;
   asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-  if (smid >= (uint32_t)kMaxSmIds) __trap();
+  if (smid >= nsmid) __trap();
   if (threadIdx.x == 0) {
     uint32_t k = 0;
     for (uint32_t tries = 0;; tries++) {
@@ -180,7 +187,7 @@ k_msm_warp_gmem(const G1Affine* __restrict__ points, const MsmRec* __restrict__ 
   const int sub = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int w = threadIdx.x & 31;
   // slot-major: the two slots normally in use on every SM form one contiguous prefix of the buffer
-  uint4* bk = scratch + (((size_t)slot * kMaxSmIds + smid) * 4 + (threadIdx.x >> 5)) * (kWarpBucketBytes / 16) + w;
+  uint4* bk = scratch + (((size_t)slot * nsmid + smid) * 4 + (threadIdx.x >> 5)) * (kWarpBucketBytes / 16) + w;
   if (sub < nsub) {
     const MsmSub s = subs[sub];
     uint32_t nonempty = 0;
@@ -242,6 +249,7 @@ k_msm_warp_gmem(const G1Affine* __restrict__ points, const MsmRec* __restrict__ 
 struct GmemScratch {
   uint4* buf = nullptr;
   uint32_t* bitmap = nullptr;
+  uint32_t nsmid = 0;       // number of %smid values on this device
   size_t hot_bytes = 0;     // prefix normally in use (2 CTA slots per SM)
   size_t persist_bytes = 0; // size of the L2 persisting carve-out this path asks for (0: unsupported)
   bool persist = false;     // the carve-out is currently set
@@ -267,14 +275,20 @@ static GmemScratch* gmem_scratch() {
   std::lock_guard<std::mutex> lk(g_scratch_mu);
   GmemScratch& g = g_scratch[dev & 63];
   if (!g.buf) {
-    int sms = 0;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms > kMaxSmIds) return nullptr;
-    size_t bytes = (size_t)kMaxSmIds * kSlotsPerSm * 4 * kWarpBucketBytes;  // %smid may skip disabled units
-    if (cudaMalloc(&g.buf, bytes) != cudaSuccess) { g.buf = nullptr; return nullptr; }
-    if (cudaMalloc(&g.bitmap, 4096) != cudaSuccess) { cudaFree(g.buf); g.buf = nullptr; return nullptr; }
+    if (cudaMalloc(&g.bitmap, 4096) != cudaSuccess) return nullptr;
     cudaMemset(g.bitmap, 0, 4096);
-    g.hot_bytes = (size_t)2 * kMaxSmIds * 4 * kWarpBucketBytes;
+    k_query_nsmid<<<1, 1>>>(g.bitmap + 1000);
+    uint32_t nsmid = 0;
+    if (cudaMemcpy(&nsmid, g.bitmap + 1000, 4, cudaMemcpyDeviceToHost) != cudaSuccess || nsmid == 0 || nsmid > 1000) {
+      cudaFree(g.bitmap);
+      cudaGetLastError();
+      return nullptr;
+    }
+    cudaMemset(g.bitmap, 0, 4096);
+    g.nsmid = nsmid;
+    size_t bytes = (size_t)nsmid * kSlotsPerSm * 4 * kWarpBucketBytes;
+    if (cudaMalloc(&g.buf, bytes) != cudaSuccess) { cudaFree(g.bitmap); g.buf = nullptr; cudaGetLastError(); return nullptr; }
+    g.hot_bytes = (size_t)2 * nsmid * 4 * kWarpBucketBytes;
     // keep the bucket scratch resident in L2: persisting carve-out + access-policy window (set per stream)
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess && prop.persistingL2CacheMaxSize > 0 && !getenv("CDL_NO_L2_PERSIST")) {
@@ -473,7 +487,7 @@ void launch_msm_tp(const G1Affine* points, const uint32_t* idx, const Fr* scalar
           cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
           (void)prop;
         }
-        k_msm_warp_gmem<<<(nsub + 3) / 4, 128, 0, st>>>(points, rec, subs, nsub, win, g->buf, g->bitmap);
+        k_msm_warp_gmem<<<(nsub + 3) / 4, 128, 0, st>>>(points, rec, subs, nsub, win, g->buf, g->bitmap, g->nsmid);
       }
     } else {
       k_msm_warp<<<(nsub + 3) / 4, 128, 0, st>>>(points, rec, subs, nsub, win);
