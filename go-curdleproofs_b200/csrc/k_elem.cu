@@ -12,7 +12,7 @@ namespace cdl {
 // stride 0: one shared scalar (Whisk rescale, IPA / SameMSM folds) — every lane
 // runs the identical digit schedule, no divergence.  Scalars arrive in gnark's
 // Montgomery fr.Element form and are brought to canonical form here.
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(64, 5)
 k_scalar_mul(const G1Affine* __restrict__ P, const Fr* __restrict__ s, int stride,
              const G1Affine* __restrict__ L, G1Affine* __restrict__ out, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -47,7 +47,8 @@ k_jac_to_affine(const G1Jac* __restrict__ in, G1Affine* __restrict__ out, int n)
 // rounds (the reference mutates its slices in place the same way,
 // innerproductargument.go:157-171).  A launch never has dst aliasing another
 // op's src/add, so ops are independent.
-__global__ void __launch_bounds__(128)
+// 64-thread CTAs, five per SM (<= 192 registers): 2.5 warps per scheduler keep the integer pipe fed
+__global__ void __launch_bounds__(64, 5)
 k_elem_ops(G1Affine* __restrict__ pool, const ElemOp* __restrict__ ops, const Fr* __restrict__ scalars, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
