@@ -264,6 +264,34 @@ def msm_sweep(ctx, pkg, log2_sizes, reps, world, rank, peak_modmul, barrier):
     return out, cpu
 
 
+def single_proof_latency(ctx, pkg, ells=(60, 124, 508)):
+    """BASELINE.json configs 1-3: curdleproof.Prove / Verify for one proof at a time through the C ABI
+    (setup of curdleproof_test.go:239-274 with perm = Rand(42).GeneratePermutation), best of 3, wall clock."""
+    out = []
+    for ell in ells:
+        r = pkg.Rand(0)
+        crs = ctx.generate_crs(ell, r)
+        k = r.get_fr()
+        Rs = ctx.rand_get_g1_affines(r, ell)
+        Ss = ctx.rand_get_g1_affines(r, ell)
+        perm = pkg.Rand(42).generate_permutation(ell)
+        Ts, Us, M, rs_m = ctx.shuffle_permute_commit(crs, Rs, Ss, perm, k, r)
+        bp = bv = None
+        for it in range(4):
+            t0 = time.perf_counter()
+            proof = ctx.prove(crs, Rs, Ss, Ts, Us, M, perm, k, rs_m, pkg.Rand(42))
+            t1 = time.perf_counter()
+            ok = ctx.verify(crs, proof, Rs, Ss, Ts, Us, M, pkg.Rand(43))
+            t2 = time.perf_counter()
+            assert ok
+            if it:
+                bp = t1 - t0 if bp is None else min(bp, t1 - t0)
+                bv = t2 - t1 if bv is None else min(bv, t2 - t1)
+        out.append({"shuffled_elements": ell, "prove_ms": bp * 1e3, "verify_ms": bv * 1e3, "proof_bytes": len(proof)})
+        crs.close()
+    return out
+
+
 def gpu_main(args):
     import torch
     import torch.distributed as dist
@@ -447,6 +475,11 @@ def gpu_main(args):
             "clocks": sampler.summary(),
         }
         line["verify_only"] = verify_only
+        if world == 1 and not args.no_latency:
+            line["single_proof"] = {"what": "curdleproof.Prove / Verify, one proof at a time (configs 1-3), wall clock",
+                                    "reference_published_ms": {"prove": [96.4, 150.2, 412.5], "verify": [12.0, 12.3, 20.8],
+                                                               "hardware": "Ryzen 7 3800XT, README.md:19-26"},
+                                    "sizes": single_proof_latency(ctx, pkg)}
         if msm is not None:
             line["msm"] = {"workload": "standalone G1 MSM, random points/scalars, device resident"
                                        + (f", windows dealt to {world} ranks + NCCL all-gather" if world > 1 else ""),
@@ -483,6 +516,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lanes", type=int, default=8, help="concurrent sub-batches per GPU (0 = library default)")
     ap.add_argument("--no-msm", action="store_true", help="skip the standalone MSM sweep")
+    ap.add_argument("--no-latency", action="store_true", help="skip the single-proof latency lines")
     ap.add_argument("--msm-sizes", default="", help="comma separated log2 sizes for the MSM sweep")
     args = ap.parse_args()
     if args.impl == "reference":
