@@ -208,3 +208,25 @@ def test_public_known_answers(ctx):
     # 1*G + 2*G + ... as one MSM: 15*G = 5*G + 10*G
     s15 = ctx.g1_msm(pts, frs_enc([1, 1, 1, 1, 1]))
     assert jac_dec(s15) == jac_dec(ctx.g1_msm(gen, fr_enc(15)))
+
+
+def test_msm_batch_multi_chunk_tasks(ctx, pts):
+    """Throughput path with tasks longer than one bucket-warp chunk (128 terms): the chunk partials
+    are summed per (task, window) before the Horner combine; also a single long MSM (> 384 terms,
+    chunked chain with 32-term chunks) next to short ones."""
+    import random
+    random.seed(12)
+    r = Rand(79)
+    from oracle.cbackend import CBackend
+    cb = CBackend(accelerate_keccak=False)
+    for sizes in ([random.choice([1, 5, 127, 128, 129, 300, 700]) for _ in range(100)], [3, 500, 0, 9]):
+        offs = [0]
+        for s in sizes:
+            offs.append(offs[-1] + s)
+        ps = [pts[random.randrange(len(pts))] for _ in range(offs[-1])]
+        ks = r.get_frs(offs[-1])
+        for i in range(0, len(ps), 41):
+            ps[i] = None
+        got = affs_dec(ctx.g1_msm_batch(affs_enc(ps), frs_enc(ks), offs))
+        want = [cb.msm(ps[offs[i]:offs[i + 1]], ks[offs[i]:offs[i + 1]]) for i in range(len(sizes))]
+        assert got == want
