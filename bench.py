@@ -380,24 +380,34 @@ def gpu_main(args):
     # trackers swapped) so that reject paths are exercised; wall clock through the C ABI
     tb = ELL * 96
     post, proofs, status = ctx.whisk_generate_shuffle_proof_batch(crs, pre, [pkg.Rand((rank << 40) | (77 << 20) | i) for i in range(B)])
-    pre_m, post_m = bytearray(pre), bytearray(post)
-    for i in range(0, B, 8):
-        pre_m[i * tb:(i + 1) * tb], post_m[i * tb:(i + 1) * tb] = post[i * tb:(i + 1) * tb], pre[i * tb:(i + 1) * tb]
-    pre_m, post_m = bytes(pre_m), bytes(post_m)
+    pre_m, post_m, proofs_m = bytearray(pre), bytearray(post), bytearray(proofs)
+    want_ok, want_st = [1] * B, [0] * B
+    for i in range(0, B, 8):  # every 8th instance is mutated, cycling through three kinds
+        kind = (i // 8) % 3
+        want_ok[i] = 0
+        if kind == 0:    # pre and post trackers swapped
+            pre_m[i * tb:(i + 1) * tb], post_m[i * tb:(i + 1) * tb] = post[i * tb:(i + 1) * tb], pre[i * tb:(i + 1) * tb]
+        elif kind == 1:  # one bit of the proof's last scalar flipped (bytes 4504..4535 of the 4576)
+            proofs_m[i * 4576 + 4535] ^= 1
+        else:            # first post-tracker point replaced by the infinity encoding: "randomizer is zero"
+            post_m[i * tb:i * tb + 48] = bytes([0xC0]) + bytes(47)
+            want_st[i] = -5
+    pre_m, post_m, proofs_m = bytes(pre_m), bytes(post_m), bytes(proofs_m)
     vt = []
     verdict_ok = True
     for it in range(3):  # first pass is the warm-up
         barrier()
         t1 = time.perf_counter()
-        vok, vst = ctx.whisk_is_valid_shuffle_proof_batch(crs, pre_m, post_m, proofs,
+        vok, vst = ctx.whisk_is_valid_shuffle_proof_batch(crs, pre_m, post_m, proofs_m,
                                                           [pkg.Rand((rank << 40) | (78 << 20) | i) for i in range(B)])
         torch.cuda.synchronize()
         vt.append(time.perf_counter() - t1)
-        verdict_ok = verdict_ok and vok == [0 if i % 8 == 0 else 1 for i in range(B)] and vst == [0] * B
+        verdict_ok = verdict_ok and vok == want_ok and vst == want_st
     tv = torch.tensor([sum(vt[1:])], dtype=torch.float64, device=f"cuda:{local}")
     if world > 1:
         dist.all_reduce(tv, op=dist.ReduceOp.MAX)
-    verify_only = {"workload": "batched IsValidWhiskShuffleProof, n=128, every 8th instance mutated",
+    verify_only = {"workload": "batched IsValidWhiskShuffleProof, n=128, every 8th instance mutated (trackers swapped / "
+                               "scalar bit flipped / infinity tracker, in turn)",
                    "value": world * B * 2 / float(tv[0]), "unit": "verifications/s", "batch_per_gpu": B,
                    "timing": "wall clock through the C ABI with host buffers, 2 batches after 1 warm-up",
                    "verdicts": "as expected" if verdict_ok else "MISMATCH"}
