@@ -42,7 +42,6 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 ELL = 124
 METRIC = "whisk_shuffle_proof_roundtrips_per_s (GenerateWhiskShuffleProof + IsValidWhiskShuffleProof, n=128)"
@@ -159,10 +158,8 @@ class ClockSampler(threading.Thread):
 
 def make_trackers(ctx, pkg, ell: int, seeds):
     """Synthetic pre-shuffle trackers (whisk_test.go generateShuffleTrackers): (r*G, k*r*G) compressed."""
-    from oracle import bls12381 as b  # constants only (generator coordinates)
-    from util import aff_enc
-
-    gen = aff_enc(b.G1_GEN)
+    enc = importlib.import_module("go-curdleproofs_b200.encoding")
+    gen = enc.aff_enc(enc.G1_GEN)
     out = []
     for s in seeds:
         r = pkg.Rand(s)
@@ -191,13 +188,13 @@ def msm_sweep(ctx, pkg, log2_sizes, reps, world, rank, peak_modmul, barrier):
     """Config 5: points P_i = a_i*G (a_i = Rand(5).GetFr), scalars Rand(6).GetFr, both replicated on
     every rank; the result is checked against (sum a_i*s_i)*G computed with host Fr arithmetic
     through a 1-point scalar multiplication on the GPU."""
-    from oracle import bls12381 as b  # constants only
-    from util import R, RR_INV, aff_enc, fr_enc
+    enc = importlib.import_module("go-curdleproofs_b200.encoding")
+    R, RR_INV, aff_enc, fr_enc = enc.R, enc.RR_INV, enc.aff_enc, enc.fr_enc
 
     nmax = 1 << max(log2_sizes)
     r5, r6 = pkg.Rand(5), pkg.Rand(6)
     dp, da, ds = ctx.dev_buffer(96 * nmax), ctx.dev_buffer(32 * nmax), ctx.dev_buffer(32 * nmax)
-    gen = aff_enc(b.G1_GEN)
+    gen = aff_enc(enc.G1_GEN)
     chunk = 1 << min(16, min(log2_sizes))
     acc = {lg: 0 for lg in log2_sizes}
     done = 0
@@ -236,8 +233,9 @@ def msm_sweep(ctx, pkg, log2_sizes, reps, world, rank, peak_modmul, barrier):
         # the same MSM on the host cores with the CPU oracle port (bucket method, windows spread over
         # threads; the reference's gnark-crypto MultiExp cannot be built here), bounded to 2^16 terms
         try:
-            from oracle.cbackend import CBackend
-            from util import RP_INV, P as FP_P
+            from oracle.cbackend import CBackend  # CPU baseline leg: the one place the GPU arm runs the oracle
+
+            RP_INV, FP_P = enc.RP_INV, enc.P
 
             lg = min(16, min(log2_sizes))
             n = 1 << lg

@@ -8,10 +8,14 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 pkg = importlib.import_module("go-curdleproofs_b200")
-from oracle import bls12381 as b  # noqa: E402
-from util import aff_enc, fr_enc  # noqa: E402
+enc = importlib.import_module("go-curdleproofs_b200.encoding")
+aff_enc, fr_enc = enc.aff_enc, enc.fr_enc
+
+
+class b:  # generator only
+    G1_GEN = enc.G1_GEN
+
 
 ctx = pkg.Context(0)
 n = 3000
