@@ -390,7 +390,6 @@ def gpu_main(args):
         else:            # first post-tracker point replaced by the infinity encoding: "randomizer is zero"
             post_m[i * tb:i * tb + 48] = bytes([0xC0]) + bytes(47)
             want_st[i] = -5
-    pre_m, post_m, proofs_m = bytes(pre_m), bytes(post_m), bytes(proofs_m)
     vt = []
     verdict_ok = True
     for it in range(3):  # first pass is the warm-up

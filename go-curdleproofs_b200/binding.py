@@ -458,23 +458,34 @@ def _ctx_whisk_is_valid(self, crs: CRS, pre: bytes, post: bytes, proof: bytes, r
     return bool(ok.value)
 
 
-def _ctx_whisk_generate_batch(self, crs: CRS, pre: bytes, rands, proof_size: int = 4576):
+def _inbuf(x):
+    """bytes pass through; writable bytes-likes (bytearray, memoryview) are wrapped without a copy."""
+    if isinstance(x, bytes):
+        return x
+    return (C.c_char * len(x)).from_buffer(x)
+
+
+def _ctx_whisk_generate_batch(self, crs: CRS, pre, rands, proof_size: int = 4576):
+    """Returns (post_trackers, proofs, status); the two buffers are bytearrays the library wrote
+    into directly (no intermediate copies: they are tens of MB for a few thousand instances)."""
     B = len(rands)
     ell = crs.ell
-    post = C.create_string_buffer(B * ell * 96)
-    proofs = C.create_string_buffer(B * proof_size)
+    post = bytearray(B * ell * 96)
+    proofs = bytearray(B * proof_size)
     status = (C.c_int32 * B)()
     rh = (C.c_void_p * B)(*[r.h for r in rands])
-    self._chk(self.lib.cdl_whisk_generate_shuffle_proof_batch(self.h, crs.h, B, pre, rh, post, proofs, proof_size, status))
-    return post.raw, proofs.raw, list(status)
+    self._chk(self.lib.cdl_whisk_generate_shuffle_proof_batch(self.h, crs.h, B, _inbuf(pre), rh, _inbuf(post), _inbuf(proofs),
+                                                              proof_size, status))
+    return post, proofs, list(status)
 
 
-def _ctx_whisk_is_valid_batch(self, crs: CRS, pre: bytes, post: bytes, proofs: bytes, rands, proof_size: int = 4576):
+def _ctx_whisk_is_valid_batch(self, crs: CRS, pre, post, proofs, rands, proof_size: int = 4576):
     B = len(rands)
     ok = (C.c_int32 * B)()
     status = (C.c_int32 * B)()
     rh = (C.c_void_p * B)(*[r.h for r in rands])
-    self._chk(self.lib.cdl_whisk_is_valid_shuffle_proof_batch(self.h, crs.h, B, pre, post, proofs, proof_size, rh, ok, status))
+    self._chk(self.lib.cdl_whisk_is_valid_shuffle_proof_batch(self.h, crs.h, B, _inbuf(pre), _inbuf(post), _inbuf(proofs),
+                                                              proof_size, rh, ok, status))
     return list(ok), list(status)
 
 
