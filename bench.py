@@ -469,7 +469,8 @@ def gpu_main(args):
             "data": "synthetic",
             "config": {"workload": "whisk_n128_roundtrip", "shuffled_elements": ELL, "proofs_per_gpu_per_step": B,
                        "parallelism": f"proof-parallel x{world}, no data-path collective",
-                       "l2": "flushed between steps (256 MiB write)",
+                       "l2": "flushed between steps (256 MiB write); the step's own working set (about 120 kB of points per "
+                             "instance) exceeds the 126 MB L2 as well",
                        "value_definition": "proofs / device busy time = union of CUDA-event kernel intervals over all lanes "
                                            "(host Fiat-Shamir excluded)",
                        "lanes": args.lanes or 4, "host_threads_cap": int(os.environ.get("CDL_HOST_THREADS", "0")),
