@@ -344,6 +344,9 @@ struct StageBuilder {
 
 inline bool is_inf_enc(const uint8_t* e) { return memcmp(e, kInfEnc, 48) == 0; }
 
+// batches of at least this many proofs derive T_2, U_2, A_2, B_2 from R and S in a second launch
+constexpr uint32_t kStep3SplitBatch = 8;
+
 }  // namespace
 
 // ------------------------------------------------------------------ ShufflePermuteCommit
@@ -723,7 +726,12 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
   // ---- step 3: R, S, T, U, same-scalar commitments, A', B_a/B_t/B_u
   // (curdleproof.go:101-122,146-148; samescalarargument.go:46-64; samemultiscalarargument.go:58-72)
   {
-    const uint32_t terms = 6 * (ell + 1) + 4 + 3 + (n) + (ell + 1) + (ell + 1);
+    // T_2 = k*R + r_t*H, U_2, A_2 = r_k*R + r_a*H, B_2 (groupcommitment.go:17-52) are linear in R and S.
+    // One proof at a time they are folded into the same launch as <k*as, Rs> + r_t*H (no dependent
+    // stage on the latency path); a batch computes R and S once and derives the four points in a
+    // second, tiny launch of two-term MSMs over (R, H) / (S, H): 2 instead of 6 MSMs of ell terms.
+    const bool split = B >= kStep3SplitBatch;
+    const uint32_t terms = (split ? 2 * ell : 6 * (ell + 1)) + 4 + 3 + (n) + (ell + 1) + (ell + 1);
     StageBuilder sb(st, B, terms, 14);
     // working vectors of the same-multiscalar argument
     for (uint32_t b = 0; b < B; b++) {
@@ -753,9 +761,10 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
       uint32_t o = base + L.scratch;
       auto lin = [&](uint32_t out, uint32_t pts, const Fr* mulby, uint32_t extra_pt, const Fr* extra_sc) {
         sl.begin(out);
-        for (uint32_t i = 0; i < ell; i++) sl.term(base + pts + i, mulby ? fr_mul(*mulby, s.as[i]) : s.as[i]);
-        if (extra_sc) sl.term(extra_pt, *extra_sc);
-        sl.end();
+        if (!split || !mulby)
+          for (uint32_t i = 0; i < ell; i++) sl.term(base + pts + i, mulby ? fr_mul(*mulby, s.as[i]) : s.as[i]);
+        if (extra_sc && !split) sl.term(extra_pt, *extra_sc);
+        sl.end();  // split: the four derived points are empty tasks here and are filled by the next launch
       };
       lin(o + 0, L.Rs, nullptr, 0, nullptr);        // R = <as, Rs>
       lin(o + 1, L.Ss, nullptr, 0, nullptr);        // S = <as, Ss>
@@ -783,9 +792,29 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
       sl.end();
     });
     if ((rc = run_msm(st))) return rc;
+    MsmStage st2;
+    StageBuilder sb2(st2, split ? B : 0, 8, 4);
+    if (split) {
+      par(B, [&](size_t b) {
+        ProveState& s = *S[b];
+        uint32_t base = L.base((uint32_t)b), o = base + L.scratch;
+        MsmSlice sl = sb2.slice((uint32_t)b);
+        auto two = [&](uint32_t out, uint32_t pt, const Fr& a, const Fr& h) {
+          sl.begin(out); sl.term(pt, a); sl.term(L.H, h); sl.end();
+        };
+        two(o + 3, o + 0, ks[b], s.r_t);   // T_2 = k*R + r_t*H
+        two(o + 5, o + 1, ks[b], s.r_u);   // U_2 = k*S + r_u*H
+        two(o + 7, o + 0, s.r_k, s.r_a);   // A_2 = r_k*R + r_a*H
+        two(o + 9, o + 1, s.r_k, s.r_b);   // B_2 = r_k*S + r_b*H
+      });
+      if ((rc = run_msm(st2))) return rc;
+    }
     par(B, [&](size_t b) {
       ProveState& s = *S[b];
-      auto out = [&](uint32_t t) { return sb.out((uint32_t)b, t); };
+      auto out = [&](uint32_t t) {
+        if (split && (t == 3 || t == 5 || t == 7 || t == 9)) return sb2.out((uint32_t)b, (t - 3) / 2);
+        return sb.out((uint32_t)b, t);
+      };
       memcpy(s.R, out(0), 48); memcpy(s.S, out(1), 48);
       memcpy(s.T1, out(2), 48); memcpy(s.T2, out(3), 48); memcpy(s.U1, out(4), 48); memcpy(s.U2, out(5), 48);
       memcpy(s.A1, out(6), 48); memcpy(s.A2, out(7), 48); memcpy(s.B1, out(8), 48); memcpy(s.B2, out(9), 48);

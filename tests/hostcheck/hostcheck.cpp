@@ -10,6 +10,8 @@ using namespace cdl;
 extern "C" {
 
 void hc_fp_mul(const Fp* a, const Fp* b, Fp* r, int n) { for (int i = 0; i < n; i++) FpM::mul(r[i], a[i], b[i]); }
+void hc_fp_sqr(const Fp* a, Fp* r, int n) { for (int i = 0; i < n; i++) FpM::sqr(r[i], a[i]); }
+void hc_fr_sqr(const Fr* a, Fr* r, int n) { for (int i = 0; i < n; i++) FrM::sqr(r[i], a[i]); }
 void hc_fp_add(const Fp* a, const Fp* b, Fp* r, int n) { for (int i = 0; i < n; i++) FpM::add(r[i], a[i], b[i]); }
 void hc_fp_sub(const Fp* a, const Fp* b, Fp* r, int n) { for (int i = 0; i < n; i++) FpM::sub(r[i], a[i], b[i]); }
 void hc_fp_neg(const Fp* a, Fp* r, int n) { for (int i = 0; i < n; i++) FpM::neg(r[i], a[i]); }

@@ -75,6 +75,23 @@ def test_fp_arithmetic(hc):
     assert list(lx) == [int(a > (P - 1) // 2) for a in A]
 
 
+def test_fp_fr_dedicated_squaring(hc):
+    """Mont::sqr (off-diagonal + diagonal products, then a pure reduction) against a*a on values that
+    stress every carry path: all-ones limbs, single-limb values, values next to p and to 2^381."""
+    random.seed(11)
+    ones = [(1 << (32 * k)) - 1 for k in range(1, 13)]
+    single = [0xffffffff << (32 * k) for k in range(12)]
+    alt = [int("ffffffff00000000" * 6, 16) % P, int("00000000ffffffff" * 6, 16), int("80000000" * 12, 16) % P,
+           int("7fffffff" * 12, 16) % P, int("ffffffff" * 12, 16) % P]
+    edge = [0, 1, 2, P - 1, P - 2, (P - 1) // 2, 2**380, 2**381 - 1 - (2**381 - 1 >= P) * (2**381 - P)]
+    vals = [v % P for v in ones + single + alt + edge] + [random.randrange(P) for _ in range(3000)]
+    assert run1(hc.hc_fp_sqr, vals) == [a * a * RP_INV % P for a in vals]
+    assert run1(hc.hc_fp_sqr, vals) == run2(hc.hc_fp_mul, vals, vals)
+    rones = [((1 << (32 * k)) - 1) % R for k in range(1, 9)]
+    rvals = rones + [0, 1, R - 1, R - 2, (R - 1) // 2] + [random.randrange(R) for _ in range(3000)]
+    assert run1(hc.hc_fr_sqr, rvals, 32) == [a * a * RR_INV % R for a in rvals]
+
+
 def test_fr_arithmetic(hc):
     random.seed(2)
     FA = [random.randrange(R) for _ in range(300)] + [0, 1, R - 1]
