@@ -349,7 +349,7 @@ int32_t cdl_prove(cdl_ctx* c, const cdl_crs* crs, const cdl_g1_affine* Rs, const
   std::vector<int32_t> status;
   std::vector<std::string> errs;
   std::vector<uint8_t> inst_enc;
-  if ((rc = E->prove(L, 1, crs, perms, ks, rsm, rands, proofs, status, errs, inst_enc))) return rc;
+  if ((rc = E->prove(L, 1, crs, perms, ks, rsm, rands, proofs, status, errs, inst_enc, false))) return rc;
   if (status[0] != CDL_OK) return c->fail(status[0], "%s", errs[0].c_str());
   *proof_len = proofs[0].size();
   if (proofs[0].size() > proof_cap) return c->fail(CDL_ERR_INVALID_ARG, "proof buffer too small: need %zu bytes", proofs[0].size());
@@ -503,7 +503,7 @@ int32_t cdl_whisk_generate_shuffle_proof_batch(cdl_ctx* c, const cdl_crs* crs, s
   std::vector<int32_t> status;
   std::vector<std::string> errs;
   std::vector<uint8_t> inst_enc;
-  if ((rc = E->prove(L, (uint32_t)B, crs, perms, ks, rsm, rands, proofs, status, errs, inst_enc))) return rc;
+  if ((rc = E->prove(L, (uint32_t)B, crs, perms, ks, rsm, rands, proofs, status, errs, inst_enc, true))) return rc;
   const size_t per_inst = (size_t)(4 * ell + 1) * 48;
   for (size_t b = 0; b < B; b++) {
     uint8_t* po = proofs_out + b * proof_cap;

@@ -446,7 +446,8 @@ void put_fr(std::vector<uint8_t>& v, const Fr& s) {
 int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std::vector<std::vector<uint32_t>>& perms,
                       const std::vector<Fr>& ks, const std::vector<std::vector<Fr>>& rs_m_in,
                       std::vector<cdl_rand*>& rands, std::vector<std::vector<uint8_t>>& proofs,
-                      std::vector<int32_t>& status, std::vector<std::string>& errs, std::vector<uint8_t>& inst_enc) {
+                      std::vector<int32_t>& status, std::vector<std::string>& errs, std::vector<uint8_t>& inst_enc,
+                      bool witness_is_ours) {
   ProfScope ptot(prof.total);
   const uint32_t ell = L.ell, n = L.n, m = L.m;
   if (n != (1u << m)) return ctx_->fail(CDL_ERR_PROTOCOL, "cs and ds are not a power of two (ell + 4 = %u)", n);
@@ -532,7 +533,7 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
   }
 
   // ---- grand-product argument (grandproductargument.go:52-92)
-  std::vector<Fr> gp_alpha(B), gp_beta(B);
+  std::vector<Fr> gp_alpha(B), gp_beta(B), gp_beta_inv(B);
   par(B, [&](size_t b) {
     ProveState& s = *S[b];
     s.tr.append_points("gprod_step1", s.Bp, 1);
@@ -556,7 +557,7 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
     if ((rc = run_msm(st))) return rc;
     for (uint32_t b = 0; b < B; b++) memcpy(S[b]->C, sb.out(b, 0), 48);
   }
-  std::vector<std::vector<Fr>> r_b_plus_alpha(B), beta_pows(B);
+  std::vector<std::vector<Fr>> r_b_plus_alpha(B);
   std::vector<Fr> beta_l1(B);
   {
     // Gs'[i] = beta^-(i+1) Gs[i], Hs'[i] = beta^-(ell+1) Hs[i]  (:94-103) -> Gp; G = Gs || Hs
@@ -572,6 +573,7 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
       gp_beta[b] = s.tr.challenge("gprod_beta");
       if (fr_is_zero(gp_beta[b])) { s.fail("beta is zero"); }
       Fr beta_inv = fr_inv(gp_beta[b]);
+      gp_beta_inv[b] = beta_inv;
       uint32_t base = L.base((uint32_t)b);
       Fr t = beta_inv;
       Fr* scb = sc.data() + b * (ell + 1);
@@ -589,24 +591,26 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
       if ((rc = copy_points(L.base(b) + L.G, L.Gs, n))) return rc;  // Gs and Hs are adjacent in the CRS image
   }
   // D, the self-check on D, B_c, B_d  (:105-177, innerproductargument.go:59-72).
-  // The reference's other self-check, msm(Gs||Hs, cs||r_cs) == C (:164-170), recomputes
-  // C = <cs, Gs> + <r_cs, Hs> (:66-73) from the very same operands: it cannot fail, so it is not
-  // launched.  msm(G', d) == D depends on the caller's B and is kept (it is the reference's error
-  // path for a witness that does not match the commitments).
+  // D = B - <beta^i, Gs'> + <alpha*beta^(ell+1), Hs'> (:132-138) with Gs'[i] = beta^-(i+1) Gs[i] and
+  // Hs'[j] = beta^-(ell+1) Hs[j] is B - beta^-1 * Gsum + alpha * Hsum term by term - the very formula
+  // the verifier uses (:243-246) - so it is computed as that three-term MSM (same point, same bytes).
+  // The reference's self-check msm(Gs||Hs, cs||r_cs) == C (:164-170) recomputes C = <cs, Gs> + <r_cs, Hs>
+  // (:66-73) from the very same operands: it cannot fail, so it is not launched.  msm(G', d) == D
+  // (:171-177) depends on the caller's M and rs_m and is the reference's error path for a witness that
+  // does not match the commitment: it is kept whenever the caller supplied them (cdl_prove), and
+  // skipped when this library computed M from rs_m itself a moment ago (the Whisk wrapper).
   std::vector<std::vector<Fr>> rs_c(B), rs_d(B);
   std::vector<std::array<uint8_t, 48>> D_enc(B);
   {
-    StageBuilder sb(st, B, 4 * n + 1, 4);
+    StageBuilder sb(st, B, 3 + (witness_is_ours ? 0 : n) + 2 * n, 4);
     par(B, [&](size_t b) {
       ProveState& s = *S[b];
       const Fr& beta = gp_beta[b];
       const Fr& alpha = gp_alpha[b];
-      // ds[i] = bs[i]*beta^(i+1) - beta^i ; betaPowers[i] = beta^i
+      // ds[i] = bs[i]*beta^(i+1) - beta^i
       s.ds.resize(ell);
-      beta_pows[b].resize(ell);
       Fr tb = FR_ONE;
       for (uint32_t i = 0; i < ell; i++) {
-        beta_pows[b][i] = tb;
         Fr nx = fr_mul(tb, beta);
         s.ds[i] = fr_sub(fr_mul(s.bs[i], nx), tb);
         tb = nx;
@@ -615,7 +619,6 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
       beta_l1[b] = fr_mul(beta_l, beta);
       std::vector<Fr> r_ds(kBlinders);
       for (uint32_t i = 0; i < kBlinders; i++) r_ds[i] = fr_mul(beta_l1[b], r_b_plus_alpha[b][i]);
-      Fr ab = fr_mul(alpha, beta_l1[b]);
       s.z = fr_sub(fr_add(fr_mul(s.r_p, beta_l1[b]), fr_mul(s.p, beta_l)), FR_ONE);
       s.cs.insert(s.cs.end(), s.r_cs.begin(), s.r_cs.end());
       s.ds.insert(s.ds.end(), r_ds.begin(), r_ds.end());
@@ -625,14 +628,15 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
       if (s.failed) { rs_c[b].assign(n, FR_ZERO); rs_d[b].assign(n, FR_ZERO); }
       uint32_t base = L.base((uint32_t)b);
       MsmSlice sl = sb.slice((uint32_t)b);
-      // D = B - <beta^i, Gs'> + <alpha*beta^(ell+1), Hs'>
+      // D = B - beta^-1 * Gsum + alpha * Hsum
       sl.begin(base + L.scratch + 1);
       sl.term(base + L.B, FR_ONE);
-      for (uint32_t i = 0; i < ell; i++) sl.term(base + L.Gp + i, fr_neg(beta_pows[b][i]));
-      for (uint32_t j = 0; j < kBlinders; j++) sl.term(base + L.Gp + ell + j, ab);
+      sl.term(L.Gsum, fr_neg(gp_beta_inv[b]));
+      sl.term(L.Hsum, alpha);
       sl.end();
       sl.begin(base + L.scratch + 3);  // msm(G', d) must equal D
-      for (uint32_t i = 0; i < n; i++) sl.term(base + L.Gp + i, s.ds[i]);
+      if (!witness_is_ours)
+        for (uint32_t i = 0; i < n; i++) sl.term(base + L.Gp + i, s.ds[i]);
       sl.end();
       sl.begin(base + L.scratch + 4);  // B_c
       for (uint32_t i = 0; i < n; i++) sl.term(base + L.G + i, rs_c[b][i]);
@@ -645,7 +649,7 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
     for (uint32_t b = 0; b < B; b++) {
       ProveState& s = *S[b];
       memcpy(D_enc[b].data(), sb.out(b, 0), 48);
-      if (memcmp(sb.out(b, 1), D_enc[b].data(), 48) != 0) s.fail("msm(G', d) != D");
+      if (!witness_is_ours && memcmp(sb.out(b, 1), D_enc[b].data(), 48) != 0) s.fail("msm(G', d) != D");
       memcpy(s.B_c, sb.out(b, 2), 48);
       memcpy(s.B_d, sb.out(b, 3), 48);
     }

@@ -95,10 +95,12 @@ class Engine {
   // curdleproof.Prove (curdleproof.go:38-197); proofs[b] receives the serialized
   // proof (curdleproof.go:358-387).  status[b] = CDL_OK or the error.
   // inst_enc receives, per instance, the encodings of Rs | Ss | Ts | Us | M.
+  // witness_is_ours: M and rs_m were produced by shuffle_permute_commit in the same call (the Whisk
+  // wrapper), so the reference's msm(G', d) == D self-check (grandproductargument.go:171-177) cannot fail.
   int32_t prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std::vector<std::vector<uint32_t>>& perms,
                 const std::vector<Fr>& ks, const std::vector<std::vector<Fr>>& rs_m, std::vector<cdl_rand*>& rands,
                 std::vector<std::vector<uint8_t>>& proofs, std::vector<int32_t>& status,
-                std::vector<std::string>& errs, std::vector<uint8_t>& inst_enc);
+                std::vector<std::string>& errs, std::vector<uint8_t>& inst_enc, bool witness_is_ours);
   // curdleproof.Verify (curdleproof.go:199-318) for proofs whose points have
   // been decompressed into PP (see parse_and_load_proofs).
   struct ParsedProof {

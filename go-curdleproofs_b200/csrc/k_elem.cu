@@ -1,6 +1,7 @@
 // Elementwise batched point kernels: scalar multiplication / base folding and
 // Jacobian -> affine.
 #define CDL_FP_MUL_CALL 1  // one shared product body: the hot loops fit the instruction caches (mont.cuh)
+#include <algorithm>
 #include <cuda_runtime.h>
 #include "g1.cuh"
 #include "launch.h"
@@ -12,59 +13,74 @@ namespace cdl {
 // stride 0: one shared scalar (Whisk rescale, IPA / SameMSM folds) — every lane
 // runs the identical digit schedule, no divergence.  Scalars arrive in gnark's
 // Montgomery fr.Element form and are brought to canonical form here.
-// E points per thread share one inversion (see k_elem_ops below).
-template <int E>
-__global__ void __launch_bounds__(64, 5)
-k_scalar_mul(const G1Affine* __restrict__ P, const Fr* __restrict__ s, int stride,
-             const G1Affine* __restrict__ L, G1Affine* __restrict__ out, int n) {
+// Shared body of the two scalar-multiplication kernels (k_elem_ops below explains the schedule):
+// a persistent grid, thread t takes items t, t + T, t + 2T, ..; every kEB consecutive items of a
+// thread are normalised with ONE inversion.  load(i, p, k, add, has_add) fetches item i.
+constexpr int kEB = 8;
+#ifndef CDL_ELEM_MINB
+#define CDL_ELEM_MINB 4  // resident 64-thread CTAs per SM the register budget is sized for (238 registers, no spills;
+                         // 5 or 6 per SM cap the kernel at 168 registers and spill 400 B in the hot loop: 7 % slower)
+#endif
+
+template <class Load, class Store>
+__device__ __forceinline__ void scalar_mul_batched(int n, Load load, Store store) {
   const int T = gridDim.x * blockDim.x;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n) return;
-  G1Jac res[E];
-  Fp pre[E];
-  Fp run;
-  FpM::set_one(run);
+  G1Jac res[kEB];  // local memory (indexed in rolled loops): 144 B per pending point
+  Fp pre[kEB];     // pre[e] = z_0 * .. * z_e over the finite results of the chunk
 #pragma unroll 1
-  for (int e = 0; e < E; e++) {
-    const int i = e * T + t;
-    if (i >= n) break;
-    Fr km = s[(size_t)i * stride], k;
-    FrM::from_mont(k, km);
-    G1Affine p = P[i];
-    G1Jac r;
-    jac_scalar_mul_glv(r, p, k.v);
-    if (L != nullptr) {
-      G1Affine l = L[i];
-      jac_add_mixed(r, r, l);
+  for (int base = t; base < n; base += kEB * T) {
+    Fp run;
+    FpM::set_one(run);
+    int cnt = 0;
+#pragma unroll 1
+    for (int e = 0; e < kEB; e++) {
+      const int i = base + e * T;
+      if (i >= n) break;
+      G1Affine p, l;
+      Fr km, k;
+      bool has_add;
+      load(i, p, km, l, has_add);
+      FrM::from_mont(k, km);
+      G1Jac r;
+      jac_scalar_mul_glv(r, p, k.v);
+      if (has_add) jac_add_mixed(r, r, l);
+      if (!jac_is_inf(r)) FpM::mul(run, run, r.z);
+      res[e] = r;
+      pre[e] = run;
+      cnt++;
     }
-    if (E == 1) {
+    Fp inv;
+    fp_inv(inv, run);
+#pragma unroll 1
+    for (int e = cnt - 1; e >= 0; e--) {
+      G1Jac r = res[e];
       G1Affine a;
-      jac_to_affine(a, r);
-      out[i] = a;
-      return;
+      if (jac_is_inf(r)) {
+        aff_set_inf(a);
+      } else {
+        Fp zi;
+        if (e > 0) FpM::mul(zi, inv, pre[e - 1]); else zi = inv;   // 1 / z_e
+        FpM::mul(inv, inv, r.z);                                   // 1 / (z_0 .. z_{e-1})
+        jac_to_affine_with_zinv(a, r, zi);
+      }
+      store(base + e * T, a);
     }
-    if (!jac_is_inf(r)) FpM::mul(run, run, r.z);
-    res[e] = r;
-    pre[e] = run;
   }
-  Fp inv;
-  fp_inv(inv, run);
-#pragma unroll 1
-  for (int e = E - 1; e >= 0; e--) {
-    const int i = e * T + t;
-    if (i >= n) continue;
-    G1Jac r = res[e];
-    G1Affine a;
-    if (jac_is_inf(r)) {
-      aff_set_inf(a);
-    } else {
-      Fp zi;
-      if (e > 0) FpM::mul(zi, inv, pre[e - 1]); else zi = inv;
-      FpM::mul(inv, inv, r.z);
-      jac_to_affine_with_zinv(a, r, zi);
-    }
-    out[i] = a;
-  }
+}
+
+__global__ void __launch_bounds__(64, CDL_ELEM_MINB)
+k_scalar_mul(const G1Affine* __restrict__ P, const Fr* __restrict__ s, int stride,
+             const G1Affine* __restrict__ L, G1Affine* __restrict__ out, int n) {
+  scalar_mul_batched(
+      n,
+      [&](int i, G1Affine& p, Fr& km, G1Affine& l, bool& has_add) {
+        km = s[(size_t)i * stride];
+        p = P[i];
+        has_add = L != nullptr;
+        if (has_add) l = L[i];
+      },
+      [&](int i, const G1Affine& a) { out[i] = a; });
 }
 
 // bls12381.BatchJacobianToAffineG1 (transcript/transcript.go:26): every thread walks E points
@@ -113,89 +129,66 @@ k_jac_to_affine(const G1Jac* __restrict__ in, G1Affine* __restrict__ out, int n)
 // rounds (the reference mutates its slices in place the same way,
 // innerproductargument.go:157-171).  A launch never has dst aliasing another
 // op's src/add, so ops are independent.
-// 64-thread CTAs, five per SM (<= 192 registers): 2.5 warps per scheduler keep the integer pipe fed.
+// 64-thread CTAs, four per SM (two warps per scheduler saturate the carry-chain pipe, profiles/r1_ilp_probe.txt).
 //
-// Normalisation: a field inversion costs as much as ~210 products (fields.cuh), a tenth of the whole
+// Normalisation: a field inversion costs as much as ~210 products (fields.cuh), 12 % of the whole
 // scalar multiplication, and a warp pays for it once whether 1 or 32 lanes invert - so sharing one
-// inversion across the lanes of a warp saves nothing.  Instead every thread works through E ops one
-// after the other (op i = e*T + t: a warp still covers 32 consecutive ops, i.e. one shared scalar and
-// a uniform digit schedule per pass), parks the Jacobian results in local memory and inverts the
-// product of its E denominators once (Montgomery's trick, bls12381.BatchJacobianToAffineG1 in the
-// reference, transcript/transcript.go:26): 3 products + 1/E inversion per point.
-template <int E>
-__global__ void __launch_bounds__(64, 5)
+// inversion across the lanes of a warp saves nothing.  Instead the grid is persistent (one wave of
+// resident CTAs), every thread works through its items t, t + T, .. (a warp still covers 32
+// consecutive ops per pass, i.e. one shared scalar and a uniform digit schedule), parks up to kEB
+// Jacobian results in local memory and inverts the product of their denominators once (Montgomery's
+// trick, bls12381.BatchJacobianToAffineG1 in the reference, transcript/transcript.go:26): 3 products
+// + 1/kEB inversion per point.  The persistent grid also removes the tail of the last wave: every
+// thread of a launch does floor or ceil of n / T equal-cost items.
+__global__ void __launch_bounds__(64, CDL_ELEM_MINB)
 k_elem_ops(G1Affine* __restrict__ pool, const ElemOp* __restrict__ ops, const Fr* __restrict__ scalars, int n) {
-  const int T = gridDim.x * blockDim.x;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n) return;
-  G1Jac res[E];   // local memory (indexed in a rolled loop); 144 B per pending point
-  Fp pre[E];      // pre[e] = z_0 * .. * z_e over the finite results
-  Fp run;
-  FpM::set_one(run);
-#pragma unroll 1
-  for (int e = 0; e < E; e++) {
-    const int i = e * T + t;
-    if (i >= n) break;
-    ElemOp op = ops[i];
-    Fr km = scalars[op.sc], k;
-    FrM::from_mont(k, km);
-    G1Affine p = pool[op.src];
-    G1Jac r;
-    jac_scalar_mul_glv(r, p, k.v);
-    if (op.add != kNoPoint) {
-      G1Affine l = pool[op.add];
-      jac_add_mixed(r, r, l);
-    }
-    if (E == 1) {
-      G1Affine a;
-      jac_to_affine(a, r);
-      pool[op.dst] = a;
-      return;
-    }
-    if (!jac_is_inf(r)) FpM::mul(run, run, r.z);
-    res[e] = r;
-    pre[e] = run;
-  }
-  Fp inv;
-  fp_inv(inv, run);
-#pragma unroll 1
-  for (int e = E - 1; e >= 0; e--) {
-    const int i = e * T + t;
-    if (i >= n) continue;
-    G1Jac r = res[e];
-    G1Affine a;
-    if (jac_is_inf(r)) {
-      aff_set_inf(a);
-    } else {
-      Fp zi;
-      if (e > 0) FpM::mul(zi, inv, pre[e - 1]); else zi = inv;   // 1 / z_e
-      FpM::mul(inv, inv, r.z);                                   // 1 / (z_0 .. z_{e-1})
-      jac_to_affine_with_zinv(a, r, zi);
-    }
-    pool[ops[i].dst] = a;
-  }
+  scalar_mul_batched(
+      n,
+      [&](int i, G1Affine& p, Fr& km, G1Affine& l, bool& has_add) {
+        const ElemOp op = ops[i];
+        km = scalars[op.sc];
+        p = pool[op.src];
+        has_add = op.add != kNoPoint;
+        if (has_add) l = pool[op.add];
+      },
+      [&](int i, const G1Affine& a) { pool[ops[i].dst] = a; });
+}
+
+// resident CTAs of a kernel on the current device (persistent-grid size)
+template <class K>
+static int resident_ctas(K kernel, int tpb) {
+  int dev = 0, sms = 0, per_sm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, tpb, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+  return sms * per_sm;
+}
+
+// Grid of a launch over n equal-cost items: with at most `resident` CTAs in flight a thread takes
+// k = ceil(n / (resident * tpb)) items; the grid is then shrunk to ceil(n / k) threads so that every
+// thread does k items (k - 1 for a few) instead of some doing k and the rest idling through the last pass.
+static int balanced_blocks(int n, int tpb, int resident) {
+  const long long tmax = (long long)resident * tpb;
+  const int k = (int)((n + tmax - 1) / tmax);
+  const int threads = (n + k - 1) / k;
+  return (threads + tpb - 1) / tpb;
 }
 
 void launch_elem_ops(G1Affine* pool, const ElemOp* ops, const Fr* scalars, int n, cudaStream_t st) {
+  if (n <= 0) return;
   const int tpb = 64;
-  // enough ops to fill the machine several times over: four per thread share one inversion
-  if (n >= 4 * 148 * 5 * tpb) {
-    const int threads = (n + 3) / 4;
-    k_elem_ops<4><<<(threads + tpb - 1) / tpb, tpb, 0, st>>>(pool, ops, scalars, n);
-  } else {
-    k_elem_ops<1><<<(n + tpb - 1) / tpb, tpb, 0, st>>>(pool, ops, scalars, n);
-  }
+  static thread_local int resident = 0;  // one device per context thread; re-queried per thread
+  if (!resident) resident = resident_ctas(k_elem_ops, tpb);
+  k_elem_ops<<<balanced_blocks(n, tpb, resident), tpb, 0, st>>>(pool, ops, scalars, n);
 }
 
 void launch_scalar_mul(const G1Affine* P, const Fr* s, int stride, const G1Affine* L, G1Affine* out, int n,
                        cudaStream_t st) {
+  if (n <= 0) return;
   const int tpb = 64;
-  if (n >= 4 * 148 * 5 * tpb) {
-    const int threads = (n + 3) / 4;
-    k_scalar_mul<4><<<(threads + tpb - 1) / tpb, tpb, 0, st>>>(P, s, stride, L, out, n);
-  } else {
-    k_scalar_mul<1><<<(n + tpb - 1) / tpb, tpb, 0, st>>>(P, s, stride, L, out, n);
-  }
+  static thread_local int resident = 0;
+  if (!resident) resident = resident_ctas(k_scalar_mul, tpb);
+  k_scalar_mul<<<balanced_blocks(n, tpb, resident), tpb, 0, st>>>(P, s, stride, L, out, n);
 }
 void launch_jac_to_affine(const G1Jac* in, G1Affine* out, int n, cudaStream_t st) {
   if (n <= 0) return;

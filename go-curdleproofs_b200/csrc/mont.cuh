@@ -169,6 +169,9 @@ struct Mont {
   // Number of limbs of E (PAR = 0) / O (PAR = 1) written before row I starts: E rows start at limb
   // 2i+2 and row i's top limb is i + jmax + 1 with jmax the largest j <= N-1 of the right parity.
   template <int PAR>
+#if defined(__CUDACC__)
+  __host__ __device__
+#endif
   static constexpr int sq_written(int I) {
     int top = PAR == 0 ? 2 : 0;  // E[0], E[1] are never written (kept zero); O starts empty
     for (int i = 0; i < I; i++) {
@@ -289,7 +292,9 @@ struct Mont {
     for (int i = 0; i < N; i++) r.v[i] = even[i];
   }
 
-#if defined(__CUDA_ARCH__) && defined(CDL_FP_MUL_CALL)
+#if defined(CDL_NO_DEDICATED_SQR)  // A/B switch for tools/kbench.cu
+  static CDL_HD void sqr(El& r, const El& a) { mul(r, a, a); }
+#elif defined(__CUDA_ARCH__) && defined(CDL_FP_MUL_CALL)
   static __device__ __noinline__ El sqr_call(El a) {
     El r;
     sqr_inline(r, a);
