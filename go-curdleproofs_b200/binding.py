@@ -90,6 +90,7 @@ def load_library():
     lib.cdl_whisk_generate_tracker_proof_batch.argtypes = [vp, sz, vp, vp, C.POINTER(vp), vp, i32p]
     lib.cdl_whisk_is_valid_tracker_proof_batch.argtypes = [vp, sz, vp, vp, vp, i32p, i32p]
     lib.cdl_host_selftest.argtypes = [vp, vp, vp, vp]
+    lib.cdl_host_selftest_fibers.argtypes = [C.c_uint32, C.c_uint32, vp, C.POINTER(C.c_int32)]
     lib.cdl_engine_stats.argtypes = [vp, vp, vp, vp, vp, C.c_int]
     lib.cdl_engine_busy_ms.argtypes = [vp, C.POINTER(C.c_double)]
     lib.cdl_set_lanes.argtypes = [vp, i32]

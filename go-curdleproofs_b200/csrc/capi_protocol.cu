@@ -212,6 +212,38 @@ int32_t cdl_host_selftest(uint8_t* out32, const cdl_fr* a, const cdl_fr* b, cdl_
   return CDL_OK;
 }
 
+int32_t cdl_host_selftest_fibers(uint32_t n, uint32_t rounds, uint8_t* digest32, int32_t* used_x8) {
+  if (!digest32 || !used_x8 || n == 0 || n > (1u << 16)) return CDL_ERR_INVALID_ARG;
+  auto work = [&](size_t i, uint8_t* out) {  // out: rounds * 32 + 32 bytes
+    cdlh::Transcript t("curdleproofs");
+    cdlh::Rand rnd(1000 + i);
+    uint8_t msg[200];
+    for (uint32_t r = 0; r < rounds; r++) {
+      size_t len = 1 + (i * 7 + r * 13) % sizeof msg;
+      for (size_t k = 0; k < len; k++) msg[k] = (uint8_t)(i + 31 * r + k);
+      t.append_message("selftest_msg", msg, len);
+      Fr c = t.challenge("selftest_challenge");
+      Fr x = rnd.get_fr();
+      t.append_scalar("selftest_rand", x);
+      cdlh::fr_to_bytes_be(out + 32 * r, cdlh::fr_add(c, x));
+    }
+    t.challenge_bytes("selftest_final", out + 32 * rounds, 32);
+  };
+  const size_t per = (size_t)rounds * 32 + 32;
+  std::vector<uint8_t> plain(n * per), fib(n * per);
+  for (size_t i = 0; i < n; i++) work(i, plain.data() + i * per);
+  *used_x8 = cdlh::fibers_available() ? 1 : 0;
+  cdlh::ThreadPool pool(3);
+  std::function<void(size_t)> fn([&](size_t i) { work(i, fib.data() + i * per); });
+  pool.parallel_for((n + 7) / 8, std::function<void(size_t)>([&](size_t g) {
+    cdlh::run_fiber_group(fn, 8 * g, n - 8 * g < 8 ? n - 8 * g : 8);
+  }));
+  cdlh::Shake256 h;
+  h.absorb(fib.data(), fib.size());
+  h.read(digest32, 32);
+  return plain == fib ? CDL_OK : CDL_ERR_INTERNAL;
+}
+
 // ------------------------------------------------------------------ Rand
 int32_t cdl_rand_new(uint64_t seed, cdl_rand** out) {
   if (!out) return CDL_ERR_INVALID_ARG;
@@ -657,7 +689,7 @@ int32_t cdl_whisk_generate_tracker_proof_batch(cdl_ctx* c, size_t B, const uint8
     for (uint32_t j = 0; j < 3; j++) src[3 * b + j] = (uint32_t)(1 + b * kTpStride + 2 + j);
   std::vector<uint8_t> enc;
   if ((rc = E->compress(src, enc))) return rc;
-  E->threads().parallel_for(B, [&](size_t b) {
+  E->par(B, [&](size_t b) {
     uint8_t* out = proofs + 128 * b;
     if (status_out[b] != CDL_OK) { memset(out, 0, 128); return; }
     const uint8_t* kG = enc.data() + 48 * (3 * b);
@@ -700,7 +732,7 @@ int32_t cdl_whisk_is_valid_tracker_proof_batch(cdl_ctx* c, size_t B, const uint8
   stage.idx.resize(4 * B);
   stage.sc.resize(4 * B);
   stage.tasks.resize(2 * B);
-  E->threads().parallel_for(B, [&](size_t b) {
+  E->par(B, [&](size_t b) {
     for (uint32_t j = 0; j < 5; j++)
       if (st[5 * b + j]) status_out[b] = CDL_ERR_DECODE;
     uint32_t base = (uint32_t)(1 + b * kTpStride);

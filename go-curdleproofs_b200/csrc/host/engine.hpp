@@ -152,10 +152,20 @@ class Engine {
     double copy = 0;   // of which: filling the pinned staging buffers
     double total = 0;  // prove + verify + shuffle_permute_commit calls
   } prof;
+  // Per-proof host work of a stage.  Eight proofs at a time share a pool thread as cooperating
+  // fibers so that their Keccak permutations run as one eight-way call (host/fiber.hpp).
   template <class F>
   void par(size_t n, F&& f) {
     double t0 = now();
-    pool_.parallel_for(n, std::function<void(size_t)>(std::forward<F>(f)));
+    std::function<void(size_t)> fn(std::forward<F>(f));
+    if (n >= 4 && fibers_available()) {
+      const size_t groups = (n + 7) / 8;
+      pool_.parallel_for(groups, std::function<void(size_t)>([&](size_t g) {
+        run_fiber_group(fn, 8 * g, n - 8 * g < 8 ? n - 8 * g : 8);
+      }));
+    } else {
+      pool_.parallel_for(n, fn);
+    }
     prof.par += now() - t0;
   }
   static double now();

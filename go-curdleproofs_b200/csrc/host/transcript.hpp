@@ -10,6 +10,7 @@
 #include <string>
 #include <vector>
 
+#include "fiber.hpp"
 #include "fr.hpp"
 
 namespace cdlh {
@@ -17,7 +18,7 @@ namespace cdlh {
 inline uint64_t rol64(uint64_t v, int n) { return (v << n) | (v >> (64 - n)); }  // n in 1..63
 
 // one round fully unrolled on 25 local lanes (generated straight-line code: theta, rho+pi, chi, iota)
-inline void keccak_f1600(uint64_t a[25]) {
+inline void keccak_f1600_plain(uint64_t a[25]) {
   static const uint64_t RC[24] = {
       0x0000000000000001ull, 0x0000000000008082ull, 0x800000000000808aull, 0x8000000080008000ull,
       0x000000000000808bull, 0x0000000080000001ull, 0x8000000080008081ull, 0x8000000000008009ull,
@@ -92,14 +93,37 @@ inline void keccak_f1600(uint64_t a[25]) {
   a[0] = s0; a[1] = s1; a[2] = s2; a[3] = s3; a[4] = s4; a[5] = s5; a[6] = s6; a[7] = s7; a[8] = s8; a[9] = s9; a[10] = s10; a[11] = s11; a[12] = s12; a[13] = s13; a[14] = s14; a[15] = s15; a[16] = s16; a[17] = s17; a[18] = s18; a[19] = s19; a[20] = s20; a[21] = s21; a[22] = s22; a[23] = s23; a[24] = s24;
 }
 
+// Every sponge goes through here: inside a fiber group the state is parked and permuted together
+// with the other proofs' states by one eight-way AVX-512 call (fiber.hpp); otherwise in place.
+inline void keccak_f1600(uint64_t a[25]) {
+  if (!fiber_keccak(a)) keccak_f1600_plain(a);
+}
+
+// dst[0..n) ^= src[0..n), eight bytes at a time
+inline void xor_bytes(uint8_t* dst, const uint8_t* src, size_t n) {
+  size_t i = 0;
+  for (; i + 8 <= n; i += 8) {
+    uint64_t a, b;
+    memcpy(&a, dst + i, 8);
+    memcpy(&b, src + i, 8);
+    a ^= b;
+    memcpy(dst + i, &a, 8);
+  }
+  for (; i < n; i++) dst[i] ^= src[i];
+}
+
 // SHAKE256 with an incremental squeeze (sha3.NewShake256: Write then Read)
 class Shake256 {
  public:
   Shake256() { memset(st_, 0, sizeof st_); }
   void absorb(const uint8_t* data, size_t n) {
     uint8_t* s = reinterpret_cast<uint8_t*>(st_);
-    for (size_t i = 0; i < n; i++) {
-      s[pos_++] ^= data[i];
+    while (n) {
+      size_t take = n < kRate - pos_ ? n : kRate - pos_;
+      xor_bytes(s + pos_, data, take);
+      pos_ += take;
+      data += take;
+      n -= take;
       if (pos_ == kRate) { keccak_f1600(st_); pos_ = 0; }
     }
   }
@@ -112,9 +136,13 @@ class Shake256 {
       pos_ = 0;
       squeezing_ = true;
     }
-    for (size_t i = 0; i < n; i++) {
+    while (n) {
       if (pos_ == kRate) { keccak_f1600(st_); pos_ = 0; }
-      out[i] = s[pos_++];
+      size_t take = n < kRate - pos_ ? n : kRate - pos_;
+      memcpy(out, s + pos_, take);
+      pos_ += take;
+      out += take;
+      n -= take;
     }
   }
 
@@ -192,16 +220,24 @@ class Strobe128 {
   }
   void absorb(const uint8_t* d, size_t n) {
     uint8_t* s = bytes();
-    for (size_t i = 0; i < n; i++) {
-      s[pos_++] ^= d[i];
+    while (n) {
+      size_t take = n < (size_t)(kR - pos_) ? n : (size_t)(kR - pos_);
+      xor_bytes(s + pos_, d, take);
+      pos_ = (uint8_t)(pos_ + take);
+      d += take;
+      n -= take;
       if (pos_ == kR) run_f();
     }
   }
   void squeeze(uint8_t* out, size_t n) {
     uint8_t* s = bytes();
-    for (size_t i = 0; i < n; i++) {
-      out[i] = s[pos_];
-      s[pos_++] = 0;
+    while (n) {
+      size_t take = n < (size_t)(kR - pos_) ? n : (size_t)(kR - pos_);
+      memcpy(out, s + pos_, take);
+      memset(s + pos_, 0, take);
+      pos_ = (uint8_t)(pos_ + take);
+      out += take;
+      n -= take;
       if (pos_ == kR) run_f();
     }
   }

@@ -198,6 +198,13 @@ int32_t cdl_whisk_is_valid_tracker_proof_batch(cdl_ctx* ctx, size_t B, const uin
  * "test protocol" challenge computed by the library's transcript code;
  * fr_out receives (a*b + a - b)^-1 * a^5 computed by the host Fr code. */
 int32_t cdl_host_selftest(uint8_t* out32, const cdl_fr* a, const cdl_fr* b, cdl_fr* fr_out);
+/* Host-side self test of the eight-way transcript hashing (no GPU needed): n Merlin transcripts and
+ * SHAKE256 streams (transcript/transcript.go, common/rand.go) with per-index messages and `rounds`
+ * rejection-sampled challenges each, run once one at a time and once as cooperating fibers whose
+ * Keccak permutations are batched eight at a time (AVX-512); digest32 receives a hash over all the
+ * challenges.  Returns CDL_OK when both runs agree byte for byte; *used_x8 tells whether the
+ * eight-way path was available on this host (0: both runs were scalar). */
+int32_t cdl_host_selftest_fibers(uint32_t n, uint32_t rounds, uint8_t* digest32, int32_t* used_x8);
 /* Per kernel class statistics of the protocol-level calls since the last reset
  * (class 0 small-MSM, 1 elementwise scalar-mul/fold, 2 decompress, 3 compress /
  * normalise): launches, CUDA-event milliseconds on the launching stream,
