@@ -372,11 +372,13 @@ int32_t Engine::shuffle_permute_commit(const Layout& L, uint32_t B, const std::v
   MsmStage st;
   StageBuilder sb(st, B, ell + kBlinders, 1);
   rs_m.assign(B, std::vector<Fr>(kBlinders));
+  std::vector<Fr> small(ell);  // fr.NewElement(j), once per call
+  for (uint32_t j = 0; j < ell; j++) small[j] = fr_from_u64(j);
   for (uint32_t b = 0; b < B; b++) {
     rands[b]->r.get_frs(rs_m[b].data(), kBlinders);
     MsmSlice s = sb.slice(b);
     s.begin(L.base(b) + L.M);
-    for (uint32_t i = 0; i < ell; i++) s.term(L.Gs + i, fr_from_u64(perms[b][i]));
+    for (uint32_t i = 0; i < ell; i++) s.term(L.Gs + i, small[perms[b][i]]);
     for (uint32_t j = 0; j < kBlinders; j++) s.term(L.Hs + j, rs_m[b][j]);
     s.end();
   }
@@ -505,8 +507,11 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
     s.beta = s.tr.challenge("same_perm_beta");
     s.bs.resize(ell);
     s.p = FR_ONE;
+    std::vector<Fr> alpha_times(ell);  // alpha * j for j < ell by repeated addition
+    alpha_times[0] = FR_ZERO;
+    for (uint32_t j = 1; j < ell; j++) alpha_times[j] = fr_add(alpha_times[j - 1], s.alpha);
     for (uint32_t i = 0; i < ell; i++) {
-      s.bs[i] = fr_add(fr_add(fr_mul(s.alpha, fr_from_u64(perms[b][i])), s.perm_as[i]), s.beta);
+      s.bs[i] = fr_add(fr_add(alpha_times[perms[b][i]], s.perm_as[i]), s.beta);
       s.p = fr_mul(s.p, s.bs[i]);
     }
     s.rs_b.resize(kBlinders);

@@ -118,8 +118,11 @@ int32_t Engine::verify(const Layout& L, uint32_t B, const cdl_crs* crs, std::vec
     s.sp_alpha = s.tr.challenge("same_perm_alpha");
     s.sp_beta = s.tr.challenge("same_perm_beta");
     s.p = FR_ONE;
-    for (uint32_t i = 0; i < ell; i++)
-      s.p = fr_mul(s.p, fr_add(fr_add(fr_mul(fr_from_u64(i), s.sp_alpha), s.sp_beta), s.as[i]));
+    Fr i_alpha = FR_ZERO;  // i * alpha
+    for (uint32_t i = 0; i < ell; i++) {
+      s.p = fr_mul(s.p, fr_add(fr_add(i_alpha, s.sp_beta), s.as[i]));
+      i_alpha = fr_add(i_alpha, s.sp_alpha);
+    }
     s.tr.append_points("gprod_step1", q.enc[w.B], 1);
     s.tr.append_scalar("gprod_step1", s.p);
     s.gp_alpha = s.tr.challenge("gprod_alpha");
@@ -174,7 +177,10 @@ int32_t Engine::verify(const Layout& L, uint32_t B, const cdl_crs* crs, std::vec
 
     // -- same-permutation: C = B - A - alpha*M ; <beta.., Gs>   (samepermutationargument.go:132-142)
     Fr a1 = rand.get_fr();
-    for (uint32_t i = 0; i < ell; i++) sGs[i] = fr_add(sGs[i], fr_mul(a1, s.sp_beta));
+    {
+      const Fr a1b = fr_mul(a1, s.sp_beta);
+      for (uint32_t i = 0; i < ell; i++) sGs[i] = a1b;
+    }
     neg_term(q.pt[w.B], a1);
     neg_term(q.pt[w.A], fr_neg(a1));
     neg_term(q.pt[w.M], fr_neg(fr_mul(a1, s.sp_alpha)));
@@ -211,17 +217,20 @@ int32_t Engine::verify(const Layout& L, uint32_t B, const cdl_crs* crs, std::vec
     }
     if (q.lens[0] != m || q.lens[1] != m || q.lens[2] != m || q.lens[3] != m) { s.fail("ipa multiexp: length mismatch"); return; }
     std::vector<Fr> gamma_inv = fr_batch_inv(gamma);
-    std::vector<Fr> sv(n, FR_ONE), svp(n, FR_ONE);
-    for (uint32_t i = 0; i < n; i++)
-      for (uint32_t j = 0; j < m; j++)
-        if (i & (1u << j)) {
-          sv[i] = fr_mul(sv[i], gamma[m - j - 1]);
-          svp[i] = fr_mul(svp[i], gamma_inv[m - j - 1]);
-        }
+    // s[i] = prod over the set bits j of i of gamma[m-j-1] (innerproductargument.go:223-234), built by
+    // doubling: one product per entry instead of one per set bit
+    std::vector<Fr> sv(n), svp(n);
+    sv[0] = svp[0] = FR_ONE;
+    for (uint32_t j = 0; j < m; j++)
+      for (uint32_t i = 0; i < (1u << j); i++) {
+        sv[i + (1u << j)] = fr_mul(sv[i], gamma[m - j - 1]);
+        svp[i + (1u << j)] = fr_mul(svp[i], gamma_inv[m - j - 1]);
+      }
     // AC1 = <gamma, L_C> + B_c + alpha*C + (alpha^2 z)*(beta*H) + <gamma^-1, R_C>  vs  c0*s on Gs||Hs, beta*d0*c0 on H
     Fr a2 = rand.get_fr();
-    for (uint32_t i = 0; i < ell; i++) sGs[i] = fr_add(sGs[i], fr_mul(a2, fr_mul(sv[i], c0)));
-    for (uint32_t j = 0; j < 4; j++) sHs[j] = fr_add(sHs[j], fr_mul(a2, fr_mul(sv[ell + j], c0)));
+    const Fr a2c0 = fr_mul(a2, c0);
+    for (uint32_t i = 0; i < ell; i++) sGs[i] = fr_add(sGs[i], fr_mul(a2c0, sv[i]));
+    for (uint32_t j = 0; j < 4; j++) sHs[j] = fr_add(sHs[j], fr_mul(a2c0, sv[ell + j]));
     sH = fr_add(sH, fr_mul(a2, fr_mul(fr_mul(ipa_beta, d0), c0)));
     for (uint32_t i = 0; i < m; i++) {
       neg_term(q.pt[w.L_C + i], fr_mul(a2, gamma[i]));
@@ -232,8 +241,9 @@ int32_t Engine::verify(const Layout& L, uint32_t B, const cdl_crs* crs, std::vec
     sH = fr_sub(sH, fr_mul(a2, fr_mul(fr_mul(fr_mul(ipa_alpha, ipa_alpha), s.z), ipa_beta)));
     // AC2 = <gamma, L_D> + B_d + alpha*D + <gamma^-1, R_D>  vs  s'*us*d0 on Gs||Hs;  D = B - beta^-1 Gsum + alpha_gp Hsum
     Fr a3 = rand.get_fr();
-    for (uint32_t i = 0; i < ell; i++) sGs[i] = fr_add(sGs[i], fr_mul(a3, fr_mul(fr_mul(svp[i], us[i]), d0)));
-    for (uint32_t j = 0; j < 4; j++) sHs[j] = fr_add(sHs[j], fr_mul(a3, fr_mul(fr_mul(svp[ell + j], us[ell + j]), d0)));
+    const Fr a3d0 = fr_mul(a3, d0);
+    for (uint32_t i = 0; i < ell; i++) sGs[i] = fr_add(sGs[i], fr_mul(a3d0, fr_mul(svp[i], us[i])));
+    for (uint32_t j = 0; j < 4; j++) sHs[j] = fr_add(sHs[j], fr_mul(a3d0, fr_mul(svp[ell + j], us[ell + j])));
     for (uint32_t i = 0; i < m; i++) {
       neg_term(q.pt[w.L_D + i], fr_mul(a3, gamma[i]));
       neg_term(q.pt[w.R_D + i], fr_mul(a3, gamma_inv[i]));
@@ -297,13 +307,11 @@ int32_t Engine::verify(const Layout& L, uint32_t B, const cdl_crs* crs, std::vec
         ch[i] = s.tr.challenge("same_msm_gamma");
       }
       std::vector<Fr> ch_inv = fr_batch_inv(ch);
+      // xs[i] = x * prod over the set bits j of i of ch[lg_n-1-j] (samemultiscalarargument.go:267-277), by doubling
       std::vector<Fr> xs(n);
-      for (uint32_t i = 0; i < n; i++) {
-        Fr t = FR_ONE;
-        for (int k = (int)lg_n - 1; k >= 0; k--)
-          if (i & (1u << (lg_n - k - 1))) t = fr_mul(t, ch[k]);
-        xs[i] = fr_mul(xf, t);
-      }
+      xs[0] = xf;
+      for (uint32_t j = 0; j < lg_n; j++)
+        for (uint32_t i = 0; i < (1u << j); i++) xs[i + (1u << j)] = fr_mul(xs[i], ch[lg_n - 1 - j]);
       // over G = Gs || Hs[0..2) || Gt || Gu with point B_a + alpha*A' + <ch, L_A> + <ch^-1, R_A>
       Fr a4 = rand.get_fr();
       for (uint32_t i = 0; i < ell; i++) sGs[i] = fr_add(sGs[i], fr_mul(a4, xs[i]));

@@ -73,32 +73,36 @@ inline Fr fr_sub(const Fr& a, const Fr& b) {
 }
 inline Fr fr_neg(const Fr& a) { return fr_is_zero(a) ? a : fr_sub(FR_ZERO, a); }
 
+// Montgomery product, CIOS with the multiplication and reduction rows interleaved.  The modulus
+// leaves its top bit clear (0x73ed.. < 2^63), so the running value never needs a fifth word
+// (the "no-carry" form gnark-crypto's generated fr.Mul uses as well).
 inline Fr fr_mul(const Fr& a, const Fr& b) {
-  uint64_t t[6] = {0, 0, 0, 0, 0, 0};
+  uint64_t t0 = 0, t1 = 0, t2 = 0, t3 = 0;
   for (int i = 0; i < 4; i++) {
-    u128 c = 0;
-    for (int j = 0; j < 4; j++) {
-      c += (u128)a.l[j] * b.l[i] + t[j];
-      t[j] = (uint64_t)c;
-      c >>= 64;
-    }
-    c += t[4];
-    t[4] = (uint64_t)c;
-    t[5] = (uint64_t)(c >> 64);
-    uint64_t m = t[0] * FR_INV;
-    c = (u128)m * FR_MOD[0] + t[0];
-    c >>= 64;
-    for (int j = 1; j < 4; j++) {
-      c += (u128)m * FR_MOD[j] + t[j];
-      t[j - 1] = (uint64_t)c;
-      c >>= 64;
-    }
-    c += t[4];
-    t[3] = (uint64_t)c;
-    t[4] = t[5] + (uint64_t)(c >> 64);
+    u128 c = (u128)a.l[0] * b.l[i] + t0;
+    uint64_t lo = (uint64_t)c, A = (uint64_t)(c >> 64);
+    const uint64_t m = lo * FR_INV;
+    u128 d = (u128)m * FR_MOD[0] + lo;
+    uint64_t C = (uint64_t)(d >> 64);
+    c = (u128)a.l[1] * b.l[i] + t1 + A;
+    A = (uint64_t)(c >> 64);
+    d = (u128)m * FR_MOD[1] + (uint64_t)c + C;
+    C = (uint64_t)(d >> 64);
+    t0 = (uint64_t)d;
+    c = (u128)a.l[2] * b.l[i] + t2 + A;
+    A = (uint64_t)(c >> 64);
+    d = (u128)m * FR_MOD[2] + (uint64_t)c + C;
+    C = (uint64_t)(d >> 64);
+    t1 = (uint64_t)d;
+    c = (u128)a.l[3] * b.l[i] + t3 + A;
+    A = (uint64_t)(c >> 64);
+    d = (u128)m * FR_MOD[3] + (uint64_t)c + C;
+    C = (uint64_t)(d >> 64);
+    t2 = (uint64_t)d;
+    t3 = C + A;
   }
-  Fr r = {{t[0], t[1], t[2], t[3]}};
-  if (t[4] || fr_geq_mod(r.l)) fr_sub_mod(r.l);
+  Fr r = {{t0, t1, t2, t3}};
+  if (fr_geq_mod(r.l)) fr_sub_mod(r.l);
   return r;
 }
 inline Fr fr_sqr(const Fr& a) { return fr_mul(a, a); }

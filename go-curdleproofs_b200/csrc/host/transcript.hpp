@@ -291,7 +291,8 @@ class Transcript {
       challenge_bytes(label, dest, 32);
       Fr c;
       if (fr_from_bytes_be_canonical(c, dest)) {
-        append_scalar(label, c);
+        // AppendScalars(label, challenge): Bytes() of a canonical value is the very string it was set from
+        append_message(label, dest, 32);
         return c;
       }
     }
