@@ -57,6 +57,7 @@ def load_library():
     lib.cdl_device_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.c_char_p, sz]
     lib.cdl_g1_msm.argtypes = [vp, vp, vp, sz, vp]
     lib.cdl_g1_msm_batch.argtypes = [vp, vp, vp, u32p, sz, vp]
+    lib.cdl_g1_msm_batch_device.argtypes = [vp, vp, vp, vp, vp, sz, vp, vp, vp]
     lib.cdl_g1_scalar_mul_affine.argtypes = [vp, vp, vp, sz, sz, vp]
     lib.cdl_g1_fold.argtypes = [vp, vp, vp, vp, sz]
     lib.cdl_g1_batch_to_affine.argtypes = [vp, vp, sz, vp]
@@ -279,6 +280,19 @@ def _ctx_dev_buffer(self, nbytes: int) -> DeviceBuffer:
 def _ctx_g1_scalar_mul_affine_device(self, d_in: DeviceBuffer, d_s: DeviceBuffer, n: int, broadcast: bool,
                                      d_out: DeviceBuffer):
     self._chk(self.lib.cdl_g1_scalar_mul_affine_device(self.h, d_in.ptr, d_s.ptr, n, 0 if broadcast else 1, d_out.ptr))
+
+
+def _ctx_g1_msm_batch_device(self, d_pool: "DeviceBuffer", idx, scalars: bytes, offsets, out_slot=None, want_affine=True,
+                             want_enc=True):
+    """Batched MSM over a device-resident pool; returns (affine bytes | None, 48-byte encodings | None)."""
+    k = len(offsets) - 1
+    ia = (C.c_uint32 * max(1, len(idx)))(*idx)
+    oa = (C.c_uint32 * (k + 1))(*offsets)
+    sa = (C.c_uint32 * k)(*out_slot) if out_slot is not None else None
+    out = C.create_string_buffer(max(1, k) * G1_AFFINE_BYTES) if want_affine else None
+    o48 = C.create_string_buffer(max(1, k) * 48) if want_enc else None
+    self._chk(self.lib.cdl_g1_msm_batch_device(self.h, d_pool.ptr, ia, scalars, oa, k, sa, out, o48))
+    return (out.raw[:k * G1_AFFINE_BYTES] if out else None), (o48.raw[:k * 48] if o48 else None)
 
 
 def _ctx_g1_fold_device(self, d_L: DeviceBuffer, d_R: DeviceBuffer, d_x: DeviceBuffer, n: int):
@@ -538,6 +552,7 @@ Context.int_peak_cfg = _ctx_int_peak_cfg
 Context.dev_buffer = _ctx_dev_buffer
 Context.g1_scalar_mul_affine_device = _ctx_g1_scalar_mul_affine_device
 Context.g1_fold_device = _ctx_g1_fold_device
+Context.g1_msm_batch_device = _ctx_g1_msm_batch_device
 Context.g1_msm_device = _ctx_g1_msm_device
 Context.set_msm_window = _ctx_set_msm_window
 Context.comm_init = _ctx_comm_init

@@ -167,6 +167,71 @@ int32_t cdl_g1_msm_batch(cdl_ctx* c, const cdl_g1_affine* points, const cdl_fr* 
   return CDL_OK;
 }
 
+// Batched MSM over a DEVICE-RESIDENT pool of bases: term t of MSM j is scalars[t] * d_pool[idx[t]]
+// (bit 31 of idx[t] negates the base), t in [offsets[j], offsets[j+1]).  Indices, scalars and offsets are
+// host arrays (what a Go-hosted orchestration computes between rounds); the bases - e.g. the folded
+// vectors of innerproductargument.go:100-172, kept in HBM with cdl_g1_fold_device - never leave the
+// device.  Result j goes to d_pool[out_slot[j]] (when out_slot != NULL; later MSMs / folds can use
+// it as a base), to out[j] in gnark's affine layout (when out != NULL) and to out48 + 48*j as the
+// compressed encoding the transcript hashes (when out48 != NULL).
+int32_t cdl_g1_msm_batch_device(cdl_ctx* c, cdl_g1_affine* d_pool, const uint32_t* idx, const cdl_fr* scalars,
+                                const uint32_t* offsets, size_t k, const uint32_t* out_slot, cdl_g1_affine* out,
+                                uint8_t* out48) {
+  if (!c || !d_pool || !offsets || (k && offsets[k] && (!idx || !scalars))) return CDL_ERR_INVALID_ARG;
+  if (k == 0) return CDL_OK;
+  std::lock_guard<std::mutex> lk(c->mu);
+  CDL_CUDA(c, cudaSetDevice(c->device));
+  const size_t total = offsets[k];
+  size_t max_terms = 0;
+  std::vector<MsmTask> tasks(k);
+  for (size_t j = 0; j < k; j++) {
+    if (offsets[j + 1] < offsets[j]) return c->fail(CDL_ERR_INVALID_ARG, "msm_batch_device: offsets not monotone");
+    tasks[j].term_off = offsets[j];
+    tasks[j].term_cnt = offsets[j + 1] - offsets[j];
+    tasks[j].out_idx = (uint32_t)j;
+    tasks[j].pad = 0;
+    if (tasks[j].term_cnt > max_terms) max_terms = tasks[j].term_cnt;
+  }
+  Fr* d_sc = (Fr*)c->buf(1, (total + 1) * sizeof(Fr));
+  uint32_t* d_idx = (uint32_t*)c->buf(2, (total + 1) * sizeof(uint32_t));
+  MsmTask* d_tasks = (MsmTask*)c->buf(3, k * sizeof(MsmTask));
+  G1Affine* d_out = (G1Affine*)c->buf(4, k * sizeof(G1Affine));
+  uint8_t* d_c48 = (uint8_t*)c->buf(0, k * 48);
+  if (!d_sc || !d_idx || !d_tasks || !d_out || !d_c48) return c->fail(CDL_ERR_CUDA, "device allocation failed");
+  if (total) {
+    CDL_CUDA(c, cudaMemcpyAsync(d_sc, scalars, total * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
+    CDL_CUDA(c, cudaMemcpyAsync(d_idx, idx, total * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  }
+  CDL_CUDA(c, cudaMemcpyAsync(d_tasks, tasks.data(), k * sizeof(MsmTask), cudaMemcpyHostToDevice, c->stream));
+  const G1Affine* pool = reinterpret_cast<const G1Affine*>(d_pool);
+  if ((int)k >= kMsmSplitThreshold || max_terms > kMsmSplitTerms) {
+    std::vector<MsmSub> subs;
+    std::vector<MsmTask2> tasks2;
+    msm_build_subs(tasks.data(), k, msm_tp_pick_chunk(total, c->sm_count), subs, tasks2);
+    MsmSub* d_subs = (MsmSub*)c->buf(5, subs.size() * sizeof(MsmSub));
+    MsmTask2* d_t2 = (MsmTask2*)c->buf(6, tasks2.size() * sizeof(MsmTask2));
+    void* d_scr = c->buf(7, msm_tp_scratch_bytes(total, subs.size(), k));
+    if (!d_subs || !d_t2 || !d_scr) return c->fail(CDL_ERR_CUDA, "device allocation failed");
+    CDL_CUDA(c, cudaMemcpyAsync(d_subs, subs.data(), subs.size() * sizeof(MsmSub), cudaMemcpyHostToDevice, c->stream));
+    CDL_CUDA(c, cudaMemcpyAsync(d_t2, tasks2.data(), tasks2.size() * sizeof(MsmTask2), cudaMemcpyHostToDevice, c->stream));
+    CDL_CUDA(c, cudaStreamSynchronize(c->stream));  // subs/tasks2 are pageable host vectors
+    launch_msm_tp(pool, d_idx, d_sc, (int)total, d_subs, (int)subs.size(), d_t2, (int)k, d_out, d_c48, d_scr, c->stream);
+  } else {
+    if (max_terms > kMsmMaxTerms) return c->fail(CDL_ERR_TOO_LARGE, "msm of %zu terms exceeds the small-MSM limit", max_terms);
+    launch_msm_small(pool, d_idx, d_sc, d_tasks, (int)k, max_terms, d_out, d_c48, c->stream);
+  }
+  CDL_CUDA(c, cudaGetLastError());
+  if (out_slot) {  // scatter the results into their pool slots (k small copies on the stream)
+    for (size_t j = 0; j < k; j++)
+      CDL_CUDA(c, cudaMemcpyAsync(reinterpret_cast<G1Affine*>(d_pool) + out_slot[j], d_out + j, sizeof(G1Affine),
+                                  cudaMemcpyDeviceToDevice, c->stream));
+  }
+  if (out) CDL_CUDA(c, cudaMemcpyAsync(out, d_out, k * sizeof(G1Affine), cudaMemcpyDeviceToHost, c->stream));
+  if (out48) CDL_CUDA(c, cudaMemcpyAsync(out48, d_c48, k * 48, cudaMemcpyDeviceToHost, c->stream));
+  CDL_CUDA(c, cudaStreamSynchronize(c->stream));
+  return CDL_OK;
+}
+
 int32_t cdl_g1_msm(cdl_ctx* c, const cdl_g1_affine* points, const cdl_fr* scalars, size_t n, cdl_g1_jac* out) {
   if (!c || !out || (n && (!points || !scalars))) return CDL_ERR_INVALID_ARG;
   if (n > kBigMsmThreshold) {  // Pippenger path (k_msm_big.cu); the small-MSM kernels serve Prove/Verify sizes

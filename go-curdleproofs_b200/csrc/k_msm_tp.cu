@@ -11,10 +11,8 @@
 //                   work on every term (the term's point is one broadcast load), so lane
 //                   efficiency is ~15/16 whatever the MSM size — unlike thread-per-bucket, whose
 //                   lanes idle on load imbalance when a window has few points per bucket.
-//                   The buckets (49 KB per warp) live in a global scratch whose regions are
-//                   reused per SM slot and pinned in L2 (see k_msm_warp_gmem).
-//   k_msm_warp / k_msm_warp_smem<>: the same walk with the buckets in local memory / in shared
-//                   memory; measured alternatives, selectable with CDL_MSM_WARP=l / j / x
+//                   The buckets (49 KB per warp) live in a per-launch global scratch that a persistent
+//                   grid reuses chunk after chunk and that stays in L2 (see k_msm_warp_gmem).
 //   k_msm_chunk_sum thread per (task, window): sums the chunk partials
 //   k_msm_combine_tp thread per task: walks the windows top-down (4 doublings + 1 addition),
 //                   normalises, stores the affine point and its 48-byte encoding.  The 124-doubling
@@ -60,7 +58,7 @@ struct alignas(16) MsmRec {
   uint32_t k1p[4];
   uint32_t k2p[4];
   uint32_t pidx;   // pool index of the base
-  uint32_t flags;  // bit 0: negate the P part, bit 1: negate the phi(P) part
+  uint32_t flags;  // bit 0: negate the P part, bit 1: negate the phi(P) part, bit 2: the base is the point at infinity
   uint32_t pad[2];
   Fp bx;           // beta * x of the base: the x coordinate of phi(P), computed once per term here
                    // instead of once per term by all 32 lanes of the bucket warp
@@ -79,133 +77,62 @@ __global__ void k_msm_recode(const G1Affine* __restrict__ points, const uint32_t
   glv_bias(r.k2p, g.k2);
   r.pidx = idx[t] & 0x7fffffffu;
   bool flip = (idx[t] >> 31) != 0;
-  r.flags = ((g.neg1 != flip) ? 1u : 0u) | ((g.neg2 != flip) ? 2u : 0u);
+  const G1Affine base = points[r.pidx];
+  r.flags = ((g.neg1 != flip) ? 1u : 0u) | ((g.neg2 != flip) ? 2u : 0u) | (aff_is_inf(base) ? 4u : 0u);
   r.pad[0] = r.pad[1] = 0;
-  Fp beta, x = points[r.pidx].x;
+  Fp beta;
   fp_set_beta(beta);
-  FpM::mul(r.bx, x, beta);
+  FpM::mul(r.bx, base.x, beta);
   rec[t] = r;
 }
 
-#ifndef CDL_WARP_MIN_CTAS
-#define CDL_WARP_MIN_CTAS 2
-#endif
-__global__ void __launch_bounds__(128, CDL_WARP_MIN_CTAS)
-k_msm_warp(const G1Affine* __restrict__ points, const MsmRec* __restrict__ rec, const MsmSub* __restrict__ subs,
-           int nsub, G1Jac* __restrict__ win) {
-  const int sub = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (sub >= nsub) return;  // whole warp
-  const int w = threadIdx.x & 31;
-  const MsmSub s = subs[sub];
-  G1Xyzz bk[8];
-  uint32_t nonempty = 0;
-#pragma unroll 1
-  for (uint32_t t = 0; t < s.term_cnt; t++) {
-    const MsmRec r = ld_stream16(rec + s.term_off + t);
-    G1Affine p = ld_stream16(points + r.pidx);
-    if (aff_is_inf(p)) continue;  // uniform across the warp
-    const Fp& bx = r.bx;
-#pragma unroll 1
-    for (int h = 0; h < 2; h++) {
-      int d = glv_digit(h == 0 ? r.k1p : r.k2p, w);
-      if (d == 0) continue;
-      bool neg = (d < 0) != (((r.flags >> h) & 1u) != 0);
-      int a = (d < 0 ? -d : d) - 1;
-      G1Affine q;
-      q.x = h == 0 ? p.x : bx;
-      q.y = p.y;
-      if (neg) FpM::neg(q.y, q.y);
-      if (!((nonempty >> a) & 1u)) {
-        xyzz_from_affine(bk[a], q);
-        nonempty |= 1u << a;
-      } else {
-        G1Xyzz b = bk[a];
-        xyzz_add_mixed(b, b, q);
-        bk[a] = b;
-      }
-    }
-  }
-  // sum_d d * B_d by the running-sum trick
-  G1Xyzz run, acc;
-  xyzz_set_inf(run);
-  xyzz_set_inf(acc);
-  // buckets above the highest non-empty one contribute nothing: start there (short chunks in the
-  // late folding rounds touch one or two buckets per window)
-#pragma unroll 1
-  for (int a = nonempty ? 31 - __clz(nonempty) : -1; a >= 0; a--) {
-    if ((nonempty >> a) & 1u) {
-      G1Xyzz b = bk[a];
-      xyzz_add(run, run, b);
-    }
-    xyzz_add(acc, acc, run);
-  }
-  G1Jac j;
-  xyzz_to_jac(j, acc);
-  win[(size_t)w * nsub + sub] = j;
-}
-
-// Same walk with the 8 buckets of every lane in SHARED memory (Jacobian, 8 x 144 B x 32 lanes =
-// 36 KB per warp, one warp per CTA, six CTAs per SM): word i of bucket a of lane l lives at
-// sm[(a*36 + i)*32 + l], so every access is bank-conflict free whatever bucket each lane picks.
-// The private-array form above keeps the buckets in local memory, whose 49 KB per warp thrash
-// L1/L2 and show up as DRAM traffic hundreds of times the algorithmic bytes.
-// Same walk with the buckets in an explicitly managed GLOBAL scratch: one 49 KB region per
-// resident warp slot (SM x CTA slot x warp), claimed from a per-SM bitmap when the CTA starts and
-// released when it ends, so that every CTA that ever runs on an SM reuses the same addresses and
-// the whole working set (resident warps x 49 KB = 58 MB) stays in L2 with ordinary write-back
-// caching.  uint4 granules, layout [bucket][granule][lane]: a warp access is 512 contiguous bytes.
-constexpr int kSlotsPerSm = 4;
-
-// %smid values are below %nsmid, which can exceed the SM count when units are fused off
-__global__ void k_query_nsmid(uint32_t* out) {
-  uint32_t n;
-  asm volatile("mov.u32 %0, %%nsmid;" : "=r"(n));
-  out[0] = n;
-}
+// Bucket warps.  The 8 XYZZ buckets of every lane (49 KB per warp) live in an explicitly managed
+// GLOBAL scratch that is part of the launch's own scratch allocation: the grid is persistent (two
+// 128-thread CTAs per SM), warp (blockIdx, warp) owns region blockIdx*4 + warp for the whole launch
+// and fetches chunks from a per-launch work counter until none are left.  Every chunk a warp ever
+// processes therefore reuses the same addresses, the working set is resident warps x 49 KB = 58 MB and
+// stays in L2 (persisting access-policy window on the launching stream), and nothing survives the
+// launch: no device-global allocator state, no spinning, nothing a faulted kernel could leave behind.
+// uint4 granules, layout [bucket][granule][lane]: a warp access is 512 contiguous bytes.
 constexpr size_t kWarpBucketBytes = 8 * sizeof(G1Xyzz) * 32;
+constexpr int kWarpsPerCta = 4;
+constexpr int kCtasPerSm = 2;
 
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(32 * kWarpsPerCta, kCtasPerSm)
 k_msm_warp_gmem(const G1Affine* __restrict__ points, const MsmRec* __restrict__ rec, const MsmSub* __restrict__ subs,
-                int nsub, G1Jac* __restrict__ win, uint4* __restrict__ scratch, uint32_t* __restrict__ bitmap,
-                uint32_t nsmid) {
-  __shared__ uint32_t slot_sh;
-  uint32_t smid;
-  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-  if (smid >= nsmid) __trap();
-  if (threadIdx.x == 0) {
-    uint32_t k = 0;
-    for (uint32_t tries = 0;; tries++) {
-      uint32_t old = atomicOr(&bitmap[smid], 1u << k);
-      if (!((old >> k) & 1u)) break;
-      k = (k + 1) % kSlotsPerSm;
-      if (tries > (1u << 22)) __trap();  // a leaked slot must surface as an error, never as a hang
-    }
-    slot_sh = k;
-  }
-  __syncthreads();
-  const uint32_t slot = slot_sh;
-  const int sub = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+                int nsub, G1Jac* __restrict__ win, uint4* __restrict__ scratch, uint32_t* __restrict__ next) {
   const int w = threadIdx.x & 31;
-  // slot-major: the two slots normally in use on every SM form one contiguous prefix of the buffer
-  uint4* bk = scratch + (((size_t)slot * nsmid + smid) * 4 + (threadIdx.x >> 5)) * (kWarpBucketBytes / 16) + w;
-  if (sub < nsub) {
+  uint4* bk = scratch + ((size_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5)) * (kWarpBucketBytes / 16) + w;
+#pragma unroll 1
+  for (;;) {
+    uint32_t sub = 0;
+    if (w == 0) sub = atomicAdd(next, 1u);
+    sub = __shfl_sync(0xffffffffu, sub, 0);
+    if (sub >= (uint32_t)nsub) break;
     const MsmSub s = subs[sub];
     uint32_t nonempty = 0;
 #pragma unroll 1
     for (uint32_t t = 0; t < s.term_cnt; t++) {
-      const MsmRec r = ld_stream16(rec + s.term_off + t);
-      G1Affine p = ld_stream16(points + r.pidx);
-      if (aff_is_inf(p)) continue;  // uniform across the warp
-      const Fp& bx = r.bx;
+      // only the digits stay in registers across the two halves; the coordinates of the half's point
+      // (x or beta*x, y: warp-uniform broadcast loads) are fetched when that half is added
+      const MsmRec* rp = rec + s.term_off + t;
+      const uint4 k1 = __ldcs(reinterpret_cast<const uint4*>(rp->k1p));
+      const uint4 k2 = __ldcs(reinterpret_cast<const uint4*>(rp->k2p));
+      const uint2 pf = __ldcs(reinterpret_cast<const uint2*>(&rp->pidx));  // pidx, flags
+      if (pf.y & 4u) continue;  // base at infinity (uniform across the warp)
 #pragma unroll 1
       for (int h = 0; h < 2; h++) {
-        int d = glv_digit(h == 0 ? r.k1p : r.k2p, w);
+        const uint4 kk = h == 0 ? k1 : k2;
+        const int wi = w >> 3;  // the lane's window sits in word wi (register selects, no local array)
+        const uint32_t word = wi == 0 ? kk.x : wi == 1 ? kk.y : wi == 2 ? kk.z : kk.w;
+        const int nib = (int)((word >> ((w & 7) * 4)) & 15u);
+        const int d = w == 31 ? nib : nib - 8;  // glv_digit()
         if (d == 0) continue;
-        bool neg = (d < 0) != (((r.flags >> h) & 1u) != 0);
+        bool neg = (d < 0) != (((pf.y >> h) & 1u) != 0);
         int a = (d < 0 ? -d : d) - 1;
         G1Affine q;
-        q.x = h == 0 ? p.x : bx;
-        q.y = p.y;
+        q.x = h == 0 ? ld_stream16(&points[pf.x].x) : ld_stream16(&rp->bx);
+        q.y = ld_stream16(&points[pf.x].y);
         if (neg) FpM::neg(q.y, q.y);
         uint4* slotp = bk + (size_t)a * 12 * 32;
         G1Xyzz b;
@@ -222,6 +149,8 @@ k_msm_warp_gmem(const G1Affine* __restrict__ points, const MsmRec* __restrict__ 
         for (int i = 0; i < 12; i++) slotp[i * 32] = bw[i];
       }
     }
+    // sum_d d * B_d by the running-sum trick, from the highest non-empty bucket down (short chunks in
+    // the late folding rounds touch one or two buckets per window)
     G1Xyzz run, acc;
     xyzz_set_inf(run);
     xyzz_set_inf(acc);
@@ -241,144 +170,49 @@ k_msm_warp_gmem(const G1Affine* __restrict__ points, const MsmRec* __restrict__ 
     xyzz_to_jac(j, acc);
     win[(size_t)w * nsub + sub] = j;
   }
-  __syncthreads();
-  if (threadIdx.x == 0) atomicAnd(&bitmap[smid], ~(1u << slot));
 }
 
-// device-wide scratch of the gmem variant, shared by every context / lane on the device
-struct GmemScratch {
-  uint4* buf = nullptr;
-  uint32_t* bitmap = nullptr;
-  uint32_t nsmid = 0;       // number of %smid values on this device
-  size_t hot_bytes = 0;     // prefix normally in use (2 CTA slots per SM)
-  size_t persist_bytes = 0; // size of the L2 persisting carve-out this path asks for (0: unsupported)
-  bool persist = false;     // the carve-out is currently set
-};
-static std::mutex g_scratch_mu;
-static GmemScratch g_scratch[64];
-
-// The persisting carve-out takes L2 away from everything else on the device, so it is only held
+// The persisting L2 carve-out takes L2 away from everything else on the device, so it is only held
 // while batched-MSM launches are being issued: the large-MSM path (whose point gathers want the
 // whole L2) releases it, the next batched launch takes it back.
-void msm_l2_carveout(bool on) {
-  int dev = 0;
-  cudaGetDevice(&dev);
-  std::lock_guard<std::mutex> lk(g_scratch_mu);
-  GmemScratch& g = g_scratch[dev & 63];
-  if (!g.persist_bytes || g.persist == on) return;
-  if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, on ? g.persist_bytes : 0) == cudaSuccess) g.persist = on;
-  cudaGetLastError();
-}
-static GmemScratch* gmem_scratch() {
-  int dev = 0;
-  cudaGetDevice(&dev);
-  std::lock_guard<std::mutex> lk(g_scratch_mu);
-  GmemScratch& g = g_scratch[dev & 63];
-  if (!g.buf) {
-    if (cudaMalloc(&g.bitmap, 4096) != cudaSuccess) return nullptr;
-    cudaMemset(g.bitmap, 0, 4096);
-    k_query_nsmid<<<1, 1>>>(g.bitmap + 1000);
-    uint32_t nsmid = 0;
-    if (cudaMemcpy(&nsmid, g.bitmap + 1000, 4, cudaMemcpyDeviceToHost) != cudaSuccess || nsmid == 0 || nsmid > 1000) {
-      cudaFree(g.bitmap);
-      cudaGetLastError();
-      return nullptr;
-    }
-    cudaMemset(g.bitmap, 0, 4096);
-    g.nsmid = nsmid;
-    size_t bytes = (size_t)nsmid * kSlotsPerSm * 4 * kWarpBucketBytes;
-    if (cudaMalloc(&g.buf, bytes) != cudaSuccess) { cudaFree(g.bitmap); g.buf = nullptr; cudaGetLastError(); return nullptr; }
-    g.hot_bytes = (size_t)2 * nsmid * 4 * kWarpBucketBytes;
-    // keep the bucket scratch resident in L2: persisting carve-out + access-policy window (set per stream)
+struct L2Persist {
+  int sms = 0;
+  size_t bytes = 0;       // carve-out this path asks for (0: unsupported / disabled)
+  int max_window = 0;
+  bool queried = false, on = false;
+};
+static std::mutex g_l2_mu;
+static L2Persist g_l2[64];
+
+static L2Persist& l2_state(int dev) {  // g_l2_mu held
+  L2Persist& g = g_l2[dev & 63];
+  if (!g.queried) {
+    g.queried = true;
+    cudaDeviceGetAttribute(&g.sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g.sms < 1) g.sms = 1;
     cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess && prop.persistingL2CacheMaxSize > 0 && !getenv("CDL_NO_L2_PERSIST")) {
-      g.persist_bytes = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, g.hot_bytes);
+    if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) {
+      const size_t hot = (size_t)g.sms * kCtasPerSm * kWarpsPerCta * kWarpBucketBytes;
+      if (prop.persistingL2CacheMaxSize > 0 && !getenv("CDL_NO_L2_PERSIST"))
+        g.bytes = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, hot);
+      cudaDeviceGetAttribute(&g.max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
     }
     cudaGetLastError();
   }
-  return &g;
+  return g;
 }
 
-template <class Bucket>
-struct SmemBucketOps;
-template <>
-struct SmemBucketOps<G1Jac> {
-  static __device__ __forceinline__ void from_affine(G1Jac& b, const G1Affine& q) { jac_from_affine(b, q); }
-  static __device__ __forceinline__ void add_mixed(G1Jac& b, const G1Affine& q) { jac_add_mixed(b, b, q); }
-  static __device__ __forceinline__ void add(G1Jac& r, const G1Jac& b) { jac_add(r, r, b); }
-  static __device__ __forceinline__ void set_inf(G1Jac& b) { jac_set_inf(b); }
-  static __device__ __forceinline__ void to_jac(G1Jac& j, const G1Jac& b) { j = b; }
-};
-template <>
-struct SmemBucketOps<G1Xyzz> {
-  static __device__ __forceinline__ void from_affine(G1Xyzz& b, const G1Affine& q) { xyzz_from_affine(b, q); }
-  static __device__ __forceinline__ void add_mixed(G1Xyzz& b, const G1Affine& q) { xyzz_add_mixed(b, b, q); }
-  static __device__ __forceinline__ void add(G1Xyzz& r, const G1Xyzz& b) { xyzz_add(r, r, b); }
-  static __device__ __forceinline__ void set_inf(G1Xyzz& b) { xyzz_set_inf(b); }
-  static __device__ __forceinline__ void to_jac(G1Jac& j, const G1Xyzz& b) { xyzz_to_jac(j, b); }
-};
-
-template <class Bucket>
-__global__ void __launch_bounds__(32)
-k_msm_warp_smem(const G1Affine* __restrict__ points, const MsmRec* __restrict__ rec,
-                const MsmSub* __restrict__ subs, int nsub, G1Jac* __restrict__ win) {
-  using Ops = SmemBucketOps<Bucket>;
-  constexpr int NW = sizeof(Bucket) / 4;
-  extern __shared__ uint32_t sm[];
-  const int sub = blockIdx.x;
-  const int w = threadIdx.x;
-  const MsmSub s = subs[sub];
-  uint32_t nonempty = 0;
-#pragma unroll 1
-  for (uint32_t t = 0; t < s.term_cnt; t++) {
-    const MsmRec r = rec[s.term_off + t];
-    G1Affine p = points[r.pidx];
-    if (aff_is_inf(p)) continue;  // uniform across the warp
-    const Fp& bx = r.bx;
-#pragma unroll 1
-    for (int h = 0; h < 2; h++) {
-      int d = glv_digit(h == 0 ? r.k1p : r.k2p, w);
-      if (d == 0) continue;
-      bool neg = (d < 0) != (((r.flags >> h) & 1u) != 0);
-      int a = (d < 0 ? -d : d) - 1;
-      G1Affine q;
-      q.x = h == 0 ? p.x : bx;
-      q.y = p.y;
-      if (neg) FpM::neg(q.y, q.y);
-      uint32_t* slot = sm + (size_t)a * NW * 32 + w;
-      Bucket b;
-      uint32_t* bw = reinterpret_cast<uint32_t*>(&b);
-      if (!((nonempty >> a) & 1u)) {
-        Ops::from_affine(b, q);
-        nonempty |= 1u << a;
-      } else {
-#pragma unroll
-        for (int i = 0; i < NW; i++) bw[i] = slot[i * 32];
-        Ops::add_mixed(b, q);
-      }
-#pragma unroll
-      for (int i = 0; i < NW; i++) slot[i * 32] = bw[i];
-    }
-  }
-  Bucket run, acc;
-  Ops::set_inf(run);
-  Ops::set_inf(acc);
-#pragma unroll 1
-  for (int a = nonempty ? 31 - __clz(nonempty) : -1; a >= 0; a--) {
-    if ((nonempty >> a) & 1u) {
-      Bucket b;
-      uint32_t* bw = reinterpret_cast<uint32_t*>(&b);
-      const uint32_t* slot = sm + (size_t)a * NW * 32 + w;
-#pragma unroll
-      for (int i = 0; i < NW; i++) bw[i] = slot[i * 32];
-      Ops::add(run, b);
-    }
-    Ops::add(acc, run);
-  }
-  G1Jac j;
-  Ops::to_jac(j, acc);
-  win[(size_t)w * nsub + sub] = j;
+void msm_l2_carveout(bool on) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(g_l2_mu);
+  L2Persist& g = l2_state(dev);
+  if (!g.bytes || g.on == on) return;
+  if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, on ? g.bytes : 0) == cudaSuccess) g.on = on;
+  cudaGetLastError();
 }
+
+static size_t bucket_scratch_bytes(int sms) { return (size_t)sms * kCtasPerSm * kWarpsPerCta * kWarpBucketBytes; }
 
 // thread per (task, window): sum of the task's chunk partials, so that the serial Horner
 // chain of k_msm_combine_tp sees one point per window however finely a task was cut
@@ -422,10 +256,15 @@ k_msm_combine_tp(const G1Jac* __restrict__ wsum, const MsmTask2* __restrict__ ta
   if (out_c48) g1_compress_dev(out_c48 + 48 * (size_t)j, a);
 }
 
+// [work counter | recoded terms | chunk window sums | task window sums | bucket scratch]
 size_t msm_tp_scratch_bytes(size_t nterm, size_t nsub, size_t ntasks) {
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   size_t rec = (nterm * sizeof(MsmRec) + 255) & ~(size_t)255;
   size_t win = (nsub * kTpWindows * sizeof(G1Jac) + 255) & ~(size_t)255;
-  return rec + win + ntasks * kTpWindows * sizeof(G1Jac);
+  size_t ws = (ntasks * kTpWindows * sizeof(G1Jac) + 255) & ~(size_t)255;
+  return 256 + rec + win + ws + bucket_scratch_bytes(sms);
 }
 
 // Chunk length for a launch.  Long chunks amortise the per-chunk bucket reduction (up to 16 full
@@ -449,49 +288,36 @@ uint32_t msm_tp_pick_chunk(size_t nterm, int sm_count) {
 void launch_msm_tp(const G1Affine* points, const uint32_t* idx, const Fr* scalars, int nterm, const MsmSub* subs,
                    int nsub, const MsmTask2* tasks, int ntasks, G1Affine* out_aff, uint8_t* out_c48, void* scratch,
                    cudaStream_t st) {
-  MsmRec* rec = (MsmRec*)scratch;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  L2Persist g;
+  {
+    std::lock_guard<std::mutex> lk(g_l2_mu);
+    g = l2_state(dev);
+  }
+  uint32_t* next = (uint32_t*)scratch;
+  MsmRec* rec = (MsmRec*)((uint8_t*)scratch + 256);
   size_t rec_bytes = ((size_t)nterm * sizeof(MsmRec) + 255) & ~(size_t)255;
   size_t win_bytes = ((size_t)nsub * kTpWindows * sizeof(G1Jac) + 255) & ~(size_t)255;
-  G1Jac* win = (G1Jac*)((uint8_t*)scratch + rec_bytes);
-  G1Jac* wsum = (G1Jac*)((uint8_t*)scratch + rec_bytes + win_bytes);
+  size_t ws_bytes = ((size_t)ntasks * kTpWindows * sizeof(G1Jac) + 255) & ~(size_t)255;
+  G1Jac* win = (G1Jac*)((uint8_t*)rec + rec_bytes);
+  G1Jac* wsum = (G1Jac*)((uint8_t*)win + win_bytes);
+  uint4* buckets = (uint4*)((uint8_t*)wsum + ws_bytes);
   if (nterm > 0) k_msm_recode<<<(nterm + 127) / 128, 128, 0, st>>>(points, idx, scalars, rec, nterm);
-  static const int variant = [] {
-    const char* e = getenv("CDL_MSM_WARP");
-    return !e ? 3 : e[0] == 'j' ? 1 : e[0] == 'x' ? 2 : e[0] == 'l' ? 0 : 3;  // default: global scratch
-  }();
   if (nsub > 0) {
-    if (variant == 1) {
-      k_msm_warp_smem<G1Jac><<<nsub, 32, 8 * sizeof(G1Jac) * 32, st>>>(points, rec, subs, nsub, win);
-    } else if (variant == 2) {
-      static const cudaError_t attr = cudaFuncSetAttribute(k_msm_warp_smem<G1Xyzz>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                           (int)(8 * sizeof(G1Xyzz) * 32));
-      (void)attr;
-      k_msm_warp_smem<G1Xyzz><<<nsub, 32, 8 * sizeof(G1Xyzz) * 32, st>>>(points, rec, subs, nsub, win);
-    } else if (variant == 3) {
-      GmemScratch* g = gmem_scratch();
-      if (!g) {  // scratch allocation failed: private (local-memory) buckets
-        k_msm_warp<<<(nsub + 3) / 4, 128, 0, st>>>(points, rec, subs, nsub, win);
-      } else {
-        if (g->persist_bytes) {
-          msm_l2_carveout(true);
-          cudaDeviceProp prop;
-          int dev = 0;
-          cudaGetDevice(&dev);
-          static int max_window = [&] { int v = 0; cudaDeviceGetAttribute(&v, cudaDevAttrMaxAccessPolicyWindowSize, dev); return v; }();
-          cudaStreamAttrValue av = {};
-          av.accessPolicyWindow.base_ptr = g->buf;
-          av.accessPolicyWindow.num_bytes = std::min<size_t>(g->hot_bytes, (size_t)max_window);
-          av.accessPolicyWindow.hitRatio = 1.0f;
-          av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-          av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-          cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
-          (void)prop;
-        }
-        k_msm_warp_gmem<<<(nsub + 3) / 4, 128, 0, st>>>(points, rec, subs, nsub, win, g->buf, g->bitmap, g->nsmid);
-      }
-    } else {
-      k_msm_warp<<<(nsub + 3) / 4, 128, 0, st>>>(points, rec, subs, nsub, win);
+    cudaMemsetAsync(next, 0, 4, st);
+    if (g.bytes) {  // keep the bucket scratch resident in L2: persisting carve-out + access-policy window
+      msm_l2_carveout(true);
+      cudaStreamAttrValue av = {};
+      av.accessPolicyWindow.base_ptr = buckets;
+      av.accessPolicyWindow.num_bytes = std::min<size_t>(bucket_scratch_bytes(g.sms), (size_t)g.max_window);
+      av.accessPolicyWindow.hitRatio = 1.0f;
+      av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
     }
+    const int ctas = std::min((nsub + kWarpsPerCta - 1) / kWarpsPerCta, g.sms * kCtasPerSm);
+    k_msm_warp_gmem<<<ctas, 32 * kWarpsPerCta, 0, st>>>(points, rec, subs, nsub, win, buckets, next);
   }
   k_msm_chunk_sum<<<(ntasks * kTpWindows + 127) / 128, 128, 0, st>>>(win, tasks, ntasks, nsub, wsum);
   k_msm_combine_tp<<<(ntasks + 63) / 64, 64, 0, st>>>(wsum, tasks, ntasks, out_aff, out_c48);

@@ -248,6 +248,18 @@ int32_t cdl_g1_scalar_mul_affine_device(cdl_ctx* ctx, const cdl_g1_affine* d_in,
  * samemultiscalarargument.go:129-135); d_x points to one fr.Element in device memory. */
 int32_t cdl_g1_fold_device(cdl_ctx* ctx, cdl_g1_affine* d_L, const cdl_g1_affine* d_R, const cdl_fr* d_x, size_t n);
 
+/* (*G1Jac).MultiExp for k independent MSMs whose BASES STAY ON THE DEVICE: term t of MSM j is
+ * scalars[t] * d_pool[idx[t]] (bit 31 of idx[t] negates the base), t in [offsets[j], offsets[j+1]).
+ * idx / scalars / offsets / out_slot are HOST arrays - what the Go orchestration computes between
+ * rounds - while d_pool is a device array of affine points (cdl_dev_alloc + cdl_dev_upload, folded in
+ * place with cdl_g1_fold_device), so the folded base vectors of innerproductargument.go:100-172 and
+ * samemultiscalarargument.go:85-140 never cross PCIe.  Result j is written to d_pool[out_slot[j]]
+ * (if out_slot != NULL), to out[j] (affine, if out != NULL) and to out48 + 48*j as the compressed
+ * encoding transcript.AppendPoints hashes (if out48 != NULL). */
+int32_t cdl_g1_msm_batch_device(cdl_ctx* ctx, cdl_g1_affine* d_pool, const uint32_t* idx, const cdl_fr* scalars,
+                                const uint32_t* offsets, size_t k, const uint32_t* out_slot, cdl_g1_affine* out,
+                                uint8_t* out48);
+
 /* (*G1Jac).MultiExp on device vectors.  part_index / part_count select the
  * windows part_index, part_index + part_count, ... of the signed-digit
  * decomposition (0 / 1 = the whole MSM); the partial sum is returned already

@@ -230,3 +230,49 @@ def test_msm_batch_multi_chunk_tasks(ctx, pts):
         got = affs_dec(ctx.g1_msm_batch(affs_enc(ps), frs_enc(ks), offs))
         want = [cb.msm(ps[offs[i]:offs[i + 1]], ks[offs[i]:offs[i + 1]]) for i in range(len(sizes))]
         assert got == want
+
+
+def test_msm_batch_over_device_resident_pool(ctx, pkg):
+    """cdl_g1_msm_batch_device: the Go-hosted form of an IPA round (innerproductargument.go:100-172) —
+    bases stay in HBM, indices / scalars come from the host, results land in pool slots, are returned
+    affine and as the 48-byte encodings the transcript hashes; then the bases are folded on the device
+    and used again.  Everything is compared with the host-pointer entry points and the oracle."""
+    import random
+
+    random.seed(21)
+    n = 16
+    pts = [b.g1_mul(b.G1_GEN, random.randrange(1, b.R)) for _ in range(n)]
+    pool = ctx.dev_buffer(96 * (n + 4))
+    pool.upload(affs_enc(pts) + bytes(96 * 4))
+    half = n // 2
+    cL = [random.randrange(b.R) for _ in range(half)]
+    cR = [random.randrange(b.R) for _ in range(half)]
+    # two MSMs of one round: <c_L, G_R> and <c_R, -G_L> (bit 31 negates), results into slots n, n+1
+    idx = [half + i for i in range(half)] + [(1 << 31) | i for i in range(half)]
+    sc = b"".join(fr_enc(x) for x in cL + cR)
+    aff, enc = ctx.g1_msm_batch_device(pool, idx, sc, [0, half, n], out_slot=[n, n + 1])
+    want0 = b.g1_msm(pts[half:], cL)
+    want1 = b.g1_neg(b.g1_msm(pts[:half], cR))
+    assert affs_dec(aff) == [want0, want1]
+    assert enc == b.g1_compress(want0) + b.g1_compress(want1)
+    assert affs_dec(pool.download(96 * 2, 96 * n)) == [want0, want1]
+    # fold the resident bases: G_L[i] += x * G_R[i], then an MSM over the folded half plus a result slot
+    x = random.randrange(1, b.R)
+    dx = ctx.dev_buffer(32)
+    dx.upload(fr_enc(x))
+    L, Rr = ctx.dev_buffer(96 * half), ctx.dev_buffer(96 * half)
+    L.upload(affs_enc(pts[:half]))
+    Rr.upload(affs_enc(pts[half:]))
+    ctx.g1_fold_device(L, Rr, dx, half)
+    folded = [b.g1_add(pts[i], b.g1_mul(pts[half + i], x)) for i in range(half)]
+    assert affs_dec(L.download(96 * half)) == folded
+    pool.upload(L.download(96 * half))  # folded bases back into the pool's first half
+    s2 = [random.randrange(b.R) for _ in range(half + 1)]
+    aff2, enc2 = ctx.g1_msm_batch_device(pool, list(range(half)) + [n], b"".join(fr_enc(v) for v in s2), [0, half + 1])
+    want2 = b.g1_add(b.g1_msm(folded, s2[:half]), b.g1_mul(want0, s2[half]))
+    assert affs_dec(aff2) == [want2] and enc2 == b.g1_compress(want2)
+    # degenerate: an empty MSM and zero scalars give infinity
+    aff3, enc3 = ctx.g1_msm_batch_device(pool, [0, 1], fr_enc(0) * 2, [0, 0, 2])
+    assert affs_dec(aff3) == [None, None] and enc3 == (bytes([0xC0]) + bytes(47)) * 2
+    for d in (pool, dx, L, Rr):
+        d.close()
