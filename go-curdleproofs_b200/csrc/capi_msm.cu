@@ -82,6 +82,10 @@ int32_t big_msm_on_device(cdl_ctx* c, const G1Affine* d_pts, const Fr* d_sc, siz
                           int normalize, G1Jac* d_out) {
   if (n >= ((size_t)1 << 30)) return c->fail(CDL_ERR_TOO_LARGE, "msm: %zu terms exceed 2^30 - 1", n);
   BigMsmDims d = big_msm_dims(n, pick_c(c, n), (int)part, (int)parts);
+  // bucket counts, scan prefixes and entry offsets are 32-bit: 2 * n * (windows owned) entries must fit
+  if (big_msm_entries(d) >= ((uint64_t)1 << 32))
+    return c->fail(CDL_ERR_TOO_LARGE, "msm: %zu terms x %d windows exceed 2^32 - 1 sorted entries; use more ranks or a wider window",
+                   n, d.nlocal);
   void* scr = c->buf(7, big_msm_scratch_bytes(d));
   if (!scr) return c->fail(CDL_ERR_CUDA, "msm scratch allocation of %zu bytes failed", big_msm_scratch_bytes(d));
   cudaError_t e = launch_big_msm(d_pts, d_sc, d, normalize, scr, c->sm_count, d_out, c->stream);
@@ -237,6 +241,13 @@ int32_t cdl_comm_destroy(cdl_ctx* c) {
 
 void cdl_comm_partition(size_t n, int32_t world, int32_t rank, int32_t window_bits, int32_t* first_window,
                         int32_t* window_step, int32_t* n_windows, int32_t* my_windows) {
+  if (world < 1 || rank < 0 || rank >= world) {  // no partition exists: report zero windows
+    if (first_window) *first_window = 0;
+    if (window_step) *window_step = 0;
+    if (n_windows) *n_windows = 0;
+    if (my_windows) *my_windows = 0;
+    return;
+  }
   int c = window_bits >= 2 ? window_bits : big_msm_pick_c(n);
   BigMsmDims d = big_msm_dims(n, c, rank, world);
   if (first_window) *first_window = d.wfirst;
@@ -247,10 +258,9 @@ void cdl_comm_partition(size_t n, int32_t world, int32_t rank, int32_t window_bi
 
 // every rank holds the full point/scalar vectors (device resident); rank r sums the
 // windows r, r + world, ...; one all-gather of the partial sums; every rank gets the result
-int32_t cdl_g1_msm_sharded_device(cdl_ctx* c, const cdl_g1_affine* d_points, const cdl_fr* d_scalars, size_t n,
-                                  cdl_g1_jac* d_out, float* kernel_ms) {
-  if (!c || !d_out || (n && (!d_points || !d_scalars))) return CDL_ERR_INVALID_ARG;
-  std::lock_guard<std::mutex> lk(c->mu);
+// caller holds c->mu
+static int32_t msm_sharded_device_locked(cdl_ctx* c, const cdl_g1_affine* d_points, const cdl_fr* d_scalars, size_t n,
+                                         cdl_g1_jac* d_out, float* kernel_ms) {
   CDL_CUDA(c, cudaSetDevice(c->device));
   const int world = c->comm_world, rank = c->comm_rank;
   if (world > 1 && !c->nccl_comm) return c->fail(CDL_ERR_INVALID_ARG, "cdl_comm_init has not been called");
@@ -264,11 +274,19 @@ int32_t cdl_g1_msm_sharded_device(cdl_ctx* c, const cdl_g1_affine* d_points, con
     G1Jac* mine = d_part + world;
     int32_t rc = big_msm_on_device(c, (const G1Affine*)d_points, (const Fr*)d_scalars, n, (uint32_t)rank,
                                    (uint32_t)world, 0, mine);
-    if (rc) return rc;
+    // A rank that failed before the collective must still enter it (the others would wait for ever): it
+    // contributes the point at infinity and returns its error afterwards; every size / allocation failure
+    // above depends only on (n, world), so in practice all ranks fail alike.
+    if (rc) cudaMemsetAsync(mine, 0, sizeof(G1Jac), c->stream);
+    const int32_t local_rc = rc;
     NcclApi* a = nccl_api();
     ncclResult_t r = a->AllGather(mine, d_part, sizeof(G1Jac), ncclChar, (ncclComm_t)c->nccl_comm, c->stream);
     if (r != ncclSuccess) return c->fail(CDL_ERR_CUDA, "ncclAllGather: %s", a->GetErrorString(r));
     launch_big_combine(d_part, world, (G1Jac*)d_out, c->stream);
+    if (local_rc) {
+      cudaStreamSynchronize(c->stream);
+      return local_rc;
+    }
   }
   CDL_CUDA(c, cudaEventRecord(c->ev1, c->stream));
   CDL_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -277,24 +295,26 @@ int32_t cdl_g1_msm_sharded_device(cdl_ctx* c, const cdl_g1_affine* d_points, con
   return CDL_OK;
 }
 
+int32_t cdl_g1_msm_sharded_device(cdl_ctx* c, const cdl_g1_affine* d_points, const cdl_fr* d_scalars, size_t n,
+                                  cdl_g1_jac* d_out, float* kernel_ms) {
+  if (!c || !d_out || (n && (!d_points || !d_scalars))) return CDL_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(c->mu);
+  return msm_sharded_device_locked(c, d_points, d_scalars, n, d_out, kernel_ms);
+}
+
 int32_t cdl_g1_msm_sharded(cdl_ctx* c, const cdl_g1_affine* points, const cdl_fr* scalars, size_t n, cdl_g1_jac* out) {
   if (!c || !out || (n && (!points || !scalars))) return CDL_ERR_INVALID_ARG;
-  G1Affine* d_pts;
-  Fr* d_sc;
-  G1Jac* d_out;
-  {
-    std::lock_guard<std::mutex> lk(c->mu);
-    CDL_CUDA(c, cudaSetDevice(c->device));
-    d_pts = (G1Affine*)c->buf(0, n * sizeof(G1Affine));
-    d_sc = (Fr*)c->buf(1, n * sizeof(Fr));
-    d_out = (G1Jac*)c->buf(4, sizeof(G1Jac));
-    if (!d_pts || !d_sc || !d_out) return c->fail(CDL_ERR_CUDA, "device allocation failed");
-    CDL_CUDA(c, cudaMemcpyAsync(d_pts, points, n * sizeof(G1Affine), cudaMemcpyHostToDevice, c->stream));
-    CDL_CUDA(c, cudaMemcpyAsync(d_sc, scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
-  }
-  int32_t rc = cdl_g1_msm_sharded_device(c, (const cdl_g1_affine*)d_pts, (const cdl_fr*)d_sc, n, (cdl_g1_jac*)d_out, nullptr);
-  if (rc) return rc;
+  // one lock across staging, MSM and download: the staging slots belong to the context
   std::lock_guard<std::mutex> lk(c->mu);
+  CDL_CUDA(c, cudaSetDevice(c->device));
+  G1Affine* d_pts = (G1Affine*)c->buf(0, n * sizeof(G1Affine));
+  Fr* d_sc = (Fr*)c->buf(1, n * sizeof(Fr));
+  G1Jac* d_out = (G1Jac*)c->buf(4, sizeof(G1Jac));
+  if (!d_pts || !d_sc || !d_out) return c->fail(CDL_ERR_CUDA, "device allocation failed");
+  CDL_CUDA(c, cudaMemcpyAsync(d_pts, points, n * sizeof(G1Affine), cudaMemcpyHostToDevice, c->stream));
+  CDL_CUDA(c, cudaMemcpyAsync(d_sc, scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
+  int32_t rc = msm_sharded_device_locked(c, (const cdl_g1_affine*)d_pts, (const cdl_fr*)d_sc, n, (cdl_g1_jac*)d_out, nullptr);
+  if (rc) return rc;
   CDL_CUDA(c, cudaMemcpyAsync(out, d_out, sizeof(G1Jac), cudaMemcpyDeviceToHost, c->stream));
   CDL_CUDA(c, cudaStreamSynchronize(c->stream));
   return CDL_OK;

@@ -92,6 +92,8 @@ constexpr size_t kBigMsmThreshold = 1024;  // cdl_g1_msm switches to the Pippeng
 int big_msm_pick_c(size_t n);
 BigMsmDims big_msm_dims(size_t n, int c, int wfirst, int wstep);
 size_t big_msm_scratch_bytes(const BigMsmDims& d);
+// sorted (point, sign) entries of a launch: both GLV halves of every term in every owned window
+inline uint64_t big_msm_entries(const BigMsmDims& d) { return 2ull * (uint64_t)d.n * (uint64_t)d.nlocal; }
 cudaError_t launch_big_msm(const G1Affine* points, const Fr* scalars, const BigMsmDims& d, int normalize,
                            void* scratch, int sm_count, G1Jac* d_out, cudaStream_t st);
 void launch_big_combine(const G1Jac* in, int n, G1Jac* out, cudaStream_t st);

@@ -42,3 +42,19 @@ def test_signed_digit_decomposition_reconstructs():
             d = signed_digits(k, c)
             assert all(-M <= x <= M for x in d)
             assert sum(x << (c * w) for w, x in enumerate(d)) == k
+
+
+def test_partition_rejects_bad_rank_and_world(pkg):
+    """cdl_comm_partition with world < 1 or rank outside [0, world) reports zero windows instead of
+    dividing by zero."""
+    for world, rank in ((0, 0), (-1, 0), (4, 4), (4, -1)):
+        assert pkg.comm_partition(1 << 16, world, rank) == (0, 0, 0, 0)
+
+
+def test_sorted_entry_count_bound():
+    """The large-MSM path indexes its sorted (point, sign) entries with 32 bits: 2 * n * windows-per-rank
+    must stay below 2^32 (big_msm_on_device returns CDL_ERR_TOO_LARGE otherwise).  At c = 16 a single
+    rank owns 8 windows, so the bound bites above 2^28 terms, well inside the accepted n < 2^30."""
+    c, W = 16, 8
+    assert 2 * (1 << 28) * W == 1 << 32
+    assert 2 * ((1 << 28) - 1) * W < 1 << 32
