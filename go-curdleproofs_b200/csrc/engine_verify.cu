@@ -7,9 +7,10 @@
 // ONE multi-scalar multiplication per proof whose result must be the point at
 // infinity (the same group equation, hence the same verdict).  The same-scalar
 // argument's four direct equalities (samescalarargument.go:92-99) are four more
-// tiny MSMs in the same launch.  Two earlier launches produce the two points
+// tiny MSMs in the same launch.  One earlier launch produces the two points
 // the verifier must feed to its transcript: A' = A + T_1 + U_1 and
-// D = B - beta^-1 Gsum + alpha Hsum.
+// D = B - beta^-1 Gsum + alpha Hsum (both depend only on proof bytes and on
+// challenges drawn before either is hashed).
 #include <algorithm>
 #include <array>
 #include <cstring>
@@ -78,26 +79,7 @@ int32_t Engine::verify(const Layout& L, uint32_t B, const cdl_crs* crs, std::vec
   for (uint32_t b = 0; b < B; b++)
     if (!pp[b].ok) S[b]->fail(pp[b].err);
 
-  // ---- launch 1: A' = A + T_1 + U_1 (transcript input of the same-multiscalar argument)
   std::vector<std::array<uint8_t, 48>> Aprime(B), Denc(B);
-  {
-    st.clear();
-    std::vector<int> slot(B, -1);
-    for (uint32_t b = 0; b < B; b++) {
-      if (S[b]->failed) continue;
-      const ParsedProof& q = pp[b];
-      Wire w(q.lens);
-      MsmTask t{(uint32_t)st.idx.size(), 3, L.base(b) + L.scratch, 0};
-      st.idx.push_back(q.pt[w.A]); st.sc.push_back(FR_ONE);
-      st.idx.push_back(q.pt[w.T1]); st.sc.push_back(FR_ONE);
-      st.idx.push_back(q.pt[w.U1]); st.sc.push_back(FR_ONE);
-      slot[b] = (int)st.tasks.size();
-      st.tasks.push_back(t);
-    }
-    if ((rc = run_msm(st))) return rc;
-    for (uint32_t b = 0; b < B; b++)
-      if (slot[b] >= 0) memcpy(Aprime[b].data(), st.out48.data() + 48 * (size_t)slot[b], 48);
-  }
 
   // ---- transcript up to the grand-product challenges (curdleproof.go:213-223,
   // samepermutationargument.go:118-130, grandproductargument.go:219-232)
@@ -133,24 +115,33 @@ int32_t Engine::verify(const Layout& L, uint32_t B, const cdl_crs* crs, std::vec
     s.gp_beta_inv = fr_inv(s.gp_beta);
   });
 
-  // ---- launch 2: D = B - beta^-1 * Gsum + alpha * Hsum   (grandproductargument.go:243-246)
+  // ---- launch 1: the two points the verifier must hash, in one launch.
+  //   D = B - beta^-1 * Gsum + alpha * Hsum   (grandproductargument.go:243-246)
+  //   A' = A + T_1 + U_1                      (curdleproof.go:268-269; hashed by the same-multiscalar argument)
   {
     st.clear();
     std::vector<int> slot(B, -1);
     for (uint32_t b = 0; b < B; b++) {
       VState& s = *S[b];
       if (s.failed) continue;
-      Wire w(pp[b].lens);
-      MsmTask t{(uint32_t)st.idx.size(), 3, L.base(b) + L.scratch + 1, 0};
-      st.idx.push_back(pp[b].pt[w.B]); st.sc.push_back(FR_ONE);
+      const ParsedProof& q = pp[b];
+      Wire w(q.lens);
+      slot[b] = (int)st.tasks.size();
+      st.tasks.push_back(MsmTask{(uint32_t)st.idx.size(), 3, L.base(b) + L.scratch + 1, 0});
+      st.idx.push_back(q.pt[w.B]); st.sc.push_back(FR_ONE);
       st.idx.push_back(L.Gsum); st.sc.push_back(fr_neg(s.gp_beta_inv));
       st.idx.push_back(L.Hsum); st.sc.push_back(s.gp_alpha);
-      slot[b] = (int)st.tasks.size();
-      st.tasks.push_back(t);
+      st.tasks.push_back(MsmTask{(uint32_t)st.idx.size(), 3, L.base(b) + L.scratch, 0});
+      st.idx.push_back(q.pt[w.A]); st.sc.push_back(FR_ONE);
+      st.idx.push_back(q.pt[w.T1]); st.sc.push_back(FR_ONE);
+      st.idx.push_back(q.pt[w.U1]); st.sc.push_back(FR_ONE);
     }
     if ((rc = run_msm(st))) return rc;
     for (uint32_t b = 0; b < B; b++)
-      if (slot[b] >= 0) memcpy(Denc[b].data(), st.out48.data() + 48 * (size_t)slot[b], 48);
+      if (slot[b] >= 0) {
+        memcpy(Denc[b].data(), st.out48.data() + 48 * (size_t)slot[b], 48);
+        memcpy(Aprime[b].data(), st.out48.data() + 48 * ((size_t)slot[b] + 1), 48);
+      }
   }
 
   // ---- rest of the transcript; build the final launch
@@ -249,7 +240,7 @@ int32_t Engine::verify(const Layout& L, uint32_t B, const cdl_crs* crs, std::vec
       neg_term(q.pt[w.R_D + i], fr_mul(a3, gamma_inv[i]));
     }
     neg_term(q.pt[w.B_d], a3);
-    neg_term(base + L.scratch + 1, fr_mul(a3, ipa_alpha));  // D from launch 2
+    neg_term(base + L.scratch + 1, fr_mul(a3, ipa_alpha));  // D from launch 1
     s.snapshot = rand;  // state the reference leaves behind when the same-scalar check fails
     s.have_snapshot = true;
 
@@ -377,7 +368,7 @@ int32_t Engine::verify(const Layout& L, uint32_t B, const cdl_crs* crs, std::vec
     sc.swap(all_sc);
   });
 
-  // ---- launch 3: the four same-scalar equalities + the collapsed accumulator per proof
+  // ---- launch 2: the four same-scalar equalities + the collapsed accumulator per proof
   st.clear();
   std::vector<int> first_task(B, -1);
   for (uint32_t b = 0; b < B; b++) {
