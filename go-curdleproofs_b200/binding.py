@@ -23,7 +23,8 @@ class CdlError(RuntimeError):
 
 
 def lib_path() -> str:
-    return os.path.join(HERE, "libcurdle_b200.so")
+    # CDL_LIB: an alternative build of the same library (A/B experiments of kernel variants)
+    return os.environ.get("CDL_LIB") or os.path.join(HERE, "libcurdle_b200.so")
 
 
 def declared_symbols():

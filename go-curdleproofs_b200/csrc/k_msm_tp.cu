@@ -96,7 +96,10 @@ __global__ void k_msm_recode(const G1Affine* __restrict__ points, const uint32_t
 // uint4 granules, layout [bucket][granule][lane]: a warp access is 512 contiguous bytes.
 constexpr size_t kWarpBucketBytes = 8 * sizeof(G1Xyzz) * 32;
 constexpr int kWarpsPerCta = 4;
-constexpr int kCtasPerSm = 2;
+#ifndef CDL_TP_CTAS_PER_SM
+#define CDL_TP_CTAS_PER_SM 2
+#endif
+constexpr int kCtasPerSm = CDL_TP_CTAS_PER_SM;
 
 __global__ void __launch_bounds__(32 * kWarpsPerCta, kCtasPerSm)
 k_msm_warp_gmem(const G1Affine* __restrict__ points, const MsmRec* __restrict__ rec, const MsmSub* __restrict__ subs,
