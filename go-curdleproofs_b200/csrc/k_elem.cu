@@ -3,7 +3,7 @@
 #define CDL_FP_MUL_CALL 1  // one shared product body: the hot loops fit the instruction caches (mont.cuh)
 #include <algorithm>
 #include <cuda_runtime.h>
-#include "g1.cuh"
+#include "quad.cuh"
 #include "launch.h"
 
 namespace cdl {
@@ -154,6 +154,63 @@ k_elem_ops(G1Affine* __restrict__ pool, const ElemOp* __restrict__ ops, const Fr
       [&](int i, const G1Affine& a) { pool[ops[i].dst] = a; });
 }
 
+// Latency form for small launches (one proof at a time: 126 .. 1 016 ops per stage): FOUR lanes per
+// op (quad.cuh).  With one thread per point a stage is one 1 950-product dependent chain (1.75 ms); the
+// quad evaluates the independent products of every doubling / addition in parallel (3 and 4 levels
+// instead of 9 and 14 products) and finishes in about a third of that.  It costs ~1.8x the issue
+// slots, so launches that fill the machine keep the thread-per-point kernel above.
+constexpr int kQuadOpsPerCta = 8;  // 32 threads, 24 KB of window tables
+
+template <class Load, class Store>
+__device__ __forceinline__ void scalar_mul_quad(int n, Load load, Store store) {
+  __shared__ G1Xyzz tab[kQuadOpsPerCta][16];
+  const Quad q;
+  const int slot = threadIdx.x >> 2;
+  const int i = blockIdx.x * kQuadOpsPerCta + slot;
+  if (i >= n) return;  // the whole quad
+  G1Affine p, l;
+  Fr km, k;
+  bool has_add;
+  load(i, p, km, l, has_add);
+  FrM::from_mont(k, km);
+  G1Xyzz r;
+  qxyzz_scalar_mul_glv(q, r, p, k.v, tab[slot]);
+  if (has_add) qxyzz_add_mixed(q, r, r, l);
+  G1Affine a;
+  qxyzz_to_affine(q, a, r);
+  if (q.lane == 0) store(i, a);
+}
+
+__global__ void __launch_bounds__(4 * kQuadOpsPerCta)
+k_elem_ops_quad(G1Affine* __restrict__ pool, const ElemOp* __restrict__ ops, const Fr* __restrict__ scalars, int n) {
+  scalar_mul_quad(
+      n,
+      [&](int i, G1Affine& p, Fr& km, G1Affine& l, bool& has_add) {
+        const ElemOp op = ops[i];
+        km = scalars[op.sc];
+        p = pool[op.src];
+        has_add = op.add != kNoPoint;
+        if (has_add) l = pool[op.add];
+      },
+      [&](int i, const G1Affine& a) { pool[ops[i].dst] = a; });
+}
+
+__global__ void __launch_bounds__(4 * kQuadOpsPerCta)
+k_scalar_mul_quad(const G1Affine* __restrict__ P, const Fr* __restrict__ s, int stride,
+                  const G1Affine* __restrict__ L, G1Affine* __restrict__ out, int n) {
+  scalar_mul_quad(
+      n,
+      [&](int i, G1Affine& p, Fr& km, G1Affine& l, bool& has_add) {
+        km = s[(size_t)i * stride];
+        p = P[i];
+        has_add = L != nullptr;
+        if (has_add) l = L[i];
+      },
+      [&](int i, const G1Affine& a) { out[i] = a; });
+}
+
+constexpr int kQuadMaxOps = 8192;  // above this the thread-per-point kernel has enough warps to hide its chains
+
 // resident CTAs of a kernel on the current device (persistent-grid size)
 template <class K>
 static int resident_ctas(K kernel, int tpb) {
@@ -176,6 +233,10 @@ static int balanced_blocks(int n, int tpb, int resident) {
 
 void launch_elem_ops(G1Affine* pool, const ElemOp* ops, const Fr* scalars, int n, cudaStream_t st) {
   if (n <= 0) return;
+  if (n <= kQuadMaxOps) {
+    k_elem_ops_quad<<<(n + kQuadOpsPerCta - 1) / kQuadOpsPerCta, 4 * kQuadOpsPerCta, 0, st>>>(pool, ops, scalars, n);
+    return;
+  }
   const int tpb = 64;
   static thread_local int resident = 0;  // one device per context thread; re-queried per thread
   if (!resident) resident = resident_ctas(k_elem_ops, tpb);
@@ -185,6 +246,10 @@ void launch_elem_ops(G1Affine* pool, const ElemOp* ops, const Fr* scalars, int n
 void launch_scalar_mul(const G1Affine* P, const Fr* s, int stride, const G1Affine* L, G1Affine* out, int n,
                        cudaStream_t st) {
   if (n <= 0) return;
+  if (n <= kQuadMaxOps) {
+    k_scalar_mul_quad<<<(n + kQuadOpsPerCta - 1) / kQuadOpsPerCta, 4 * kQuadOpsPerCta, 0, st>>>(P, s, stride, L, out, n);
+    return;
+  }
   const int tpb = 64;
   static thread_local int resident = 0;
   if (!resident) resident = resident_ctas(k_scalar_mul, tpb);

@@ -17,10 +17,12 @@
 //   3. reduce   : sum_d d*B_d per window as suffix scan + butterfly over the 8
 //                 lanes of a window with warp shuffles (6 adds instead of 16).
 //   4. combine  : binary tree over windows, level L doubles the upper operand
-//                 4*2^L times (124 doublings on the critical path, 5 adds).
+//                 4*2^L times (124 doublings on the critical path, 5 adds), a quad of
+//                 lanes per pair (quad.cuh: warp-cooperative doubling / addition).
 //   5. normalise: one inversion, affine result (+ optional compressed bytes).
 #define CDL_FP_MUL_CALL 1  // one shared product body: the hot loops fit the instruction caches (mont.cuh)
 #include "codec.cuh"
+#include "quad.cuh"
 #include "launch.h"
 
 namespace cdl {
@@ -123,44 +125,47 @@ k_msm_small(const G1Affine* __restrict__ points, const uint32_t* __restrict__ id
   G1Xyzz acc;
   msm_bucket_phases(points, idx, scalars, task, smem_raw, acc);
 
-  // ---- phase 4: combine windows (Jacobian: cheaper doublings)
+  // ---- phase 4: combine windows.  Binary tree over the 32 window sums, level L doubles the upper
+  // operand 4 * 2^L times: 124 doublings + 5 additions on the critical path.  Every pair is handled by
+  // a QUAD of lanes (quad.cuh): the independent products of a doubling / addition run in parallel
+  // lanes, three / four product latencies instead of nine / fourteen.
   __syncthreads();  // the recode staging is dead from here on; reuse shared memory
-  G1Jac* win = reinterpret_cast<G1Jac*>(smem_raw);
-  if ((tid & 7) == 0) {
-    G1Jac j;
-    xyzz_to_jac(j, acc);
-    win[w] = j;
-  }
+  G1Xyzz* win = reinterpret_cast<G1Xyzz*>(smem_raw);
+  if ((tid & 7) == 0) win[w] = acc;
   __syncthreads();
+  const Quad q;
+  const int g = tid >> 2;  // 64 quads per CTA
 #pragma unroll 1
   for (int level = 0, active = kMsmWindows / 2; active >= 1; level++, active >>= 1) {
-    G1Jac lo, hi;
-    if (tid < active) {
-      lo = win[2 * tid];
-      hi = win[2 * tid + 1];
+    G1Xyzz lo, hi;
+    if (g < active) {
+      lo = win[2 * g];
+      hi = win[2 * g + 1];
       int nd = kMsmC << level;
 #pragma unroll 1
-      for (int i = 0; i < nd; i++) jac_dbl(hi, hi);
-      jac_add(lo, lo, hi);
+      for (int i = 0; i < nd; i++) qxyzz_dbl(q, hi, hi);
+      qxyzz_add(q, lo, lo, hi);
     }
     __syncthreads();
-    if (tid < active) win[tid] = lo;
+    if (g < active && q.lane == 0) win[g] = lo;
     __syncthreads();
   }
 
   // ---- phase 5: normalise + store
-  if (tid == 0) {
+  if (g == 0) {
     G1Affine a;
-    jac_to_affine(a, win[0]);
-    if (out_aff) out_aff[task.out_idx] = a;
-    if (out_c48) g1_compress_dev(out_c48 + 48 * (size_t)blockIdx.x, a);
+    qxyzz_to_affine(q, a, win[0]);
+    if (q.lane == 0) {
+      if (out_aff) out_aff[task.out_idx] = a;
+      if (out_c48) g1_compress_dev(out_c48 + 48 * (size_t)blockIdx.x, a);
+    }
   }
 }
 
 // shared memory bytes for the largest task of a launch
 static size_t msm_small_smem_bytes(size_t max_terms) {
   size_t a = max_terms * 36;                       // kp + pidx
-  size_t b = (size_t)kMsmWindows * sizeof(G1Jac);  // combine scratch
+  size_t b = (size_t)kMsmWindows * sizeof(G1Xyzz);  // combine scratch
   return a > b ? a : b;
 }
 

@@ -27,6 +27,7 @@
 // its partial sum already shifted, so the exchange is one all-gather of one point
 // per rank (k_big_combine adds them).
 #define CDL_FP_MUL_CALL 1  // one shared product body: the hot loops fit the instruction caches (mont.cuh)
+#include "quad.cuh"
 #include "launch.h"
 
 namespace cdl {
@@ -408,30 +409,34 @@ k_big_sum(const G1Xyzz* __restrict__ in, int pin, int G, int pout, int total_out
   out[t] = acc;
 }
 
-// acc = sum_j 2^(c*(wfirst + j*wstep)) * S_j ; optional normalisation to (x, y, 1) / (1, 1, 0)
+// acc = sum_j 2^(c*(wfirst + j*wstep)) * S_j ; optional normalisation to (x, y, 1) / (1, 1, 0).
+// The chain is serial by nature (c * W doublings), so it runs on one QUAD of lanes (quad.cuh): three
+// product latencies per doubling instead of nine.
 __global__ void k_big_horner(const G1Xyzz* __restrict__ S, BigMsmDims dm, int normalize, G1Jac* __restrict__ out) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  G1Jac acc;
-  jac_set_inf(acc);
+  if (threadIdx.x >= 4 || blockIdx.x != 0) return;
+  const Quad q;
+  G1Xyzz acc;
+  xyzz_set_inf(acc);
 #pragma unroll 1
   for (int j = dm.nlocal - 1; j >= 0; j--) {
     if (j != dm.nlocal - 1) {
 #pragma unroll 1
-      for (int k = 0; k < dm.c * dm.wstep; k++) jac_dbl(acc, acc);
+      for (int k = 0; k < dm.c * dm.wstep; k++) qxyzz_dbl(q, acc, acc);
     }
-    G1Xyzz s = S[j];
-    G1Jac sj;
-    xyzz_to_jac(sj, s);
-    jac_add(acc, acc, sj);
+    const G1Xyzz s = S[j];
+    qxyzz_add(q, acc, acc, s);
   }
 #pragma unroll 1
-  for (int k = 0; k < dm.c * dm.wfirst; k++) jac_dbl(acc, acc);
+  for (int k = 0; k < dm.c * dm.wfirst; k++) qxyzz_dbl(q, acc, acc);
+  G1Jac r;
   if (normalize) {
     G1Affine a;
-    jac_to_affine(a, acc);
-    jac_from_affine(acc, a);
+    qxyzz_to_affine(q, a, acc);
+    jac_from_affine(r, a);
+  } else {
+    xyzz_to_jac(r, acc);
   }
-  out[0] = acc;
+  if (q.lane == 0) out[0] = r;
 }
 
 // out = sum of n Jacobian points (the per-rank partial sums), normalised

@@ -24,6 +24,7 @@
 
 #define CDL_FP_MUL_CALL 1
 #include "codec.cuh"
+#include "quad.cuh"
 #include "launch.h"
 
 namespace cdl {
@@ -259,6 +260,47 @@ k_msm_combine_tp(const G1Jac* __restrict__ wsum, const MsmTask2* __restrict__ ta
   if (out_c48) g1_compress_dev(out_c48 + 48 * (size_t)j, a);
 }
 
+// The same Horner walk with a QUAD of lanes per task (quad.cuh) for launches with few tasks (one proof
+// at a time): 124 x 3 + 32 x 4 product latencies instead of 124 x 7 + 32 x 16.
+__global__ void __launch_bounds__(32)
+k_msm_combine_quad(const G1Jac* __restrict__ wsum, const MsmTask2* __restrict__ tasks, int ntasks,
+                   G1Affine* __restrict__ out_aff, uint8_t* __restrict__ out_c48) {
+  const Quad q;
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 2);
+  if (j >= ntasks) return;  // the whole quad
+  const MsmTask2 task = tasks[j];
+  G1Xyzz acc;
+  xyzz_set_inf(acc);
+#pragma unroll 1
+  for (int w = kTpWindows - 1; w >= 0; w--) {
+    if (w != kTpWindows - 1) {
+#pragma unroll 1
+      for (int i = 0; i < 4; i++) qxyzz_dbl(q, acc, acc);
+    }
+    const G1Jac s = wsum[(size_t)w * ntasks + j];
+    if (!jac_is_inf(s)) {  // Jacobian -> XYZZ: ZZ = Z^2, ZZZ = Z^3
+      G1Xyzz sx;
+      Fp a[4], b[4], o[4];
+      a[0] = s.z; b[0] = s.z;
+      qmul<1>(q, o, a, b);
+      sx.zz = o[0];
+      a[0] = o[0]; b[0] = s.z;
+      qmul<1>(q, o, a, b);
+      sx.zzz = o[0];
+      sx.x = s.x;
+      sx.y = s.y;
+      qxyzz_add(q, acc, acc, sx);
+    }
+  }
+  G1Affine a;
+  qxyzz_to_affine(q, a, acc);
+  if (q.lane == 0) {
+    if (out_aff) out_aff[task.out_idx] = a;
+    if (out_c48) g1_compress_dev(out_c48 + 48 * (size_t)j, a);
+  }
+}
+constexpr int kCombineQuadMaxTasks = 256;
+
 // [work counter | recoded terms | chunk window sums | task window sums | bucket scratch]
 size_t msm_tp_scratch_bytes(size_t nterm, size_t nsub, size_t ntasks) {
   int dev = 0, sms = 0;
@@ -323,7 +365,8 @@ void launch_msm_tp(const G1Affine* points, const uint32_t* idx, const Fr* scalar
     k_msm_warp_gmem<<<ctas, 32 * kWarpsPerCta, 0, st>>>(points, rec, subs, nsub, win, buckets, next);
   }
   k_msm_chunk_sum<<<(ntasks * kTpWindows + 127) / 128, 128, 0, st>>>(win, tasks, ntasks, nsub, wsum);
-  k_msm_combine_tp<<<(ntasks + 63) / 64, 64, 0, st>>>(wsum, tasks, ntasks, out_aff, out_c48);
+  if (ntasks <= kCombineQuadMaxTasks) k_msm_combine_quad<<<(ntasks + 7) / 8, 32, 0, st>>>(wsum, tasks, ntasks, out_aff, out_c48);
+  else k_msm_combine_tp<<<(ntasks + 63) / 64, 64, 0, st>>>(wsum, tasks, ntasks, out_aff, out_c48);
 }
 
 }  // namespace cdl
