@@ -97,6 +97,7 @@ int32_t begin_call(cdl_ctx* c, const cdl_crs* crs, size_t B, Engine** E, Layout*
   CDL_CUDA(c, cudaSetDevice(c->device));
   *E = engine_of(c);
   *L = Layout(crs->ell);
+  c->spin_wait = B < 8 && c->parent == nullptr;  // latency regime: see cdl_ctx::sync_stream
   int32_t rc = (*E)->ensure_pool((size_t)L->crs_size + B * (size_t)L->inst_size);
   if (rc) return rc;
   return (*E)->load_crs(*L, crs);

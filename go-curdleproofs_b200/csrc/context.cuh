@@ -19,7 +19,11 @@ struct cdl_ctx {
   cudaEvent_t ev_sync = nullptr;  // cudaEventBlockingSync: waiting host threads sleep instead of spinning
   // Wait for everything queued on the stream.  Lanes and ranks share the host cores with the
   // Fiat-Shamir work, so a waiting thread must not burn one (cudaStreamSynchronize spins).
+  // A call that serves one proof at a time is a chain of ~50 dependent stages: there the wake-up latency of
+  // a sleeping wait (tens of microseconds per stage) is on the critical path and the thread spins instead.
+  bool spin_wait = false;
   cudaError_t sync_stream() {
+    if (spin_wait) return cudaStreamSynchronize(stream);
     if (!ev_sync && cudaEventCreateWithFlags(&ev_sync, cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess)
       return cudaStreamSynchronize(stream);
     cudaError_t e = cudaEventRecord(ev_sync, stream);

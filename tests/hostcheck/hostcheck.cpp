@@ -16,6 +16,7 @@ void hc_fp_add(const Fp* a, const Fp* b, Fp* r, int n) { for (int i = 0; i < n; 
 void hc_fp_sub(const Fp* a, const Fp* b, Fp* r, int n) { for (int i = 0; i < n; i++) FpM::sub(r[i], a[i], b[i]); }
 void hc_fp_neg(const Fp* a, Fp* r, int n) { for (int i = 0; i < n; i++) FpM::neg(r[i], a[i]); }
 void hc_fp_inv(const Fp* a, Fp* r, int n) { for (int i = 0; i < n; i++) fp_inv(r[i], a[i]); }
+void hc_fp_inv_eea(const Fp* a, Fp* r, int n) { for (int i = 0; i < n; i++) fp_inv_eea(r[i], a[i]); }
 void hc_fp_sqrt(const Fp* a, Fp* r, int* ok, int n) { for (int i = 0; i < n; i++) ok[i] = fp_sqrt(r[i], a[i]); }
 void hc_fp_from_mont(const Fp* a, Fp* r, int n) { for (int i = 0; i < n; i++) FpM::from_mont(r[i], a[i]); }
 void hc_fp_to_mont(const Fp* a, Fp* r, int n) { for (int i = 0; i < n; i++) FpM::to_mont(r[i], a[i]); }

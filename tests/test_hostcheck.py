@@ -63,6 +63,10 @@ def test_fp_arithmetic(hc):
     assert run1(hc.hc_fp_to_mont, A) == [tom(a) for a in A]
     S = edge + [1 << k for k in (1, 31, 32, 63, 64, 380)] + A[:200]  # inversion: every edge value incl. 0
     assert run1(hc.hc_fp_inv, [tom(a) for a in S]) == [tom(pow(a, P - 2, P)) for a in S]
+    # the approximate-GCD inversion against the limb-wide binary Euclid it replaced, on raw residues of every size
+    T = S + [random.randrange(1 << k) for k in (8, 31, 32, 33, 62, 63, 64, 65, 96, 127, 190, 255, 320, 379) for _ in range(40)]
+    T = [t % P for t in T]
+    assert run1(hc.hc_fp_inv, T) == run1(hc.hc_fp_inv_eea, T) == [pow(t * RP_INV % P, P - 2, P) * RP % P for t in T]
     ok = (ctypes.c_int * len(S))()
     out = ctypes.create_string_buffer(48 * len(S))
     hc.hc_fp_sqrt(pack([tom(a * a % P) for a in S], 48), out, ok, len(S))
