@@ -272,8 +272,25 @@ static int32_t msm_sharded_device_locked(cdl_ctx* c, const cdl_g1_affine* d_poin
     if (rc) return rc;
   } else {
     G1Jac* mine = d_part + world;
-    int32_t rc = big_msm_on_device(c, (const G1Affine*)d_points, (const Fr*)d_scalars, n, (uint32_t)rank,
-                                   (uint32_t)world, 0, mine);
+    // Two ways to split one MSM over the ranks.  Windows: rank r sums the windows r,
+    // r + world, .. of every term (the digit passes and the sort still visit all n terms on every
+    // rank).  Points: rank r runs a complete MSM over its n / world terms.  Windows are dealt while
+    // every rank gets at least four of them; with fewer (W = 8 windows at c = 16: four ranks or more)
+    // the per-rank fixed passes and the serial tail dominate and the points are partitioned instead.
+    // Either way the exchange is one all-gather of one partial sum per rank.
+    static const int forced = [] {
+      const char* e = getenv("CDL_MSM_PARTITION");
+      return !e ? 0 : e[0] == 'p' ? 1 : e[0] == 'w' ? 2 : 0;
+    }();
+    const BigMsmDims whole = big_msm_dims(n, pick_c(c, n), 0, 1);
+    const bool by_points = forced ? forced == 1 : whole.W < 4 * world;
+    int32_t rc;
+    if (by_points) {
+      const size_t lo = n * (size_t)rank / (size_t)world, hi = n * (size_t)(rank + 1) / (size_t)world;
+      rc = big_msm_on_device(c, (const G1Affine*)d_points + lo, (const Fr*)d_scalars + lo, hi - lo, 0, 1, 0, mine);
+    } else {
+      rc = big_msm_on_device(c, (const G1Affine*)d_points, (const Fr*)d_scalars, n, (uint32_t)rank, (uint32_t)world, 0, mine);
+    }
     // A rank that failed before the collective must still enter it (the others would wait for ever): it
     // contributes the point at infinity and returns its error afterwards; every size / allocation failure
     // above depends only on (n, world), so in practice all ranks fail alike.

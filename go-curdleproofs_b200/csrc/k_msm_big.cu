@@ -392,6 +392,64 @@ k_big_reduce1(const G1Xyzz* __restrict__ buckets, int M, int L, int nchunks_tota
   out[t] = acc;
 }
 
+// The same two reductions with a QUAD of lanes per output (quad.cuh), for small MSMs: with a few hundred
+// outputs the serial chains above (30 and 16 group operations) are pure latency; a quad runs each
+// addition in four product latencies instead of fourteen.
+__device__ __forceinline__ void qxyzz_mul_small(const Quad& q, G1Xyzz& r, const G1Xyzz& p, uint32_t e) {
+  xyzz_set_inf(r);
+  if (e == 0) return;
+  int top = 31 - __clz(e);
+  r = p;
+#pragma unroll 1
+  for (int i = top - 1; i >= 0; i--) {
+    qxyzz_dbl(q, r, r);
+    if ((e >> i) & 1u) qxyzz_add(q, r, r, p);
+  }
+}
+
+__global__ void __launch_bounds__(128)
+k_big_reduce1_quad(const G1Xyzz* __restrict__ buckets, int M, int L, int nchunks_total, G1Xyzz* __restrict__ out) {
+  const Quad q;
+  int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+  if (t >= nchunks_total) return;  // the whole quad
+  const int per = M / L;
+  const int j = t / per, ch = t - j * per;
+  const G1Xyzz* B = buckets + (size_t)j * M + (size_t)ch * L;
+  G1Xyzz run, acc;
+  xyzz_set_inf(run);
+  xyzz_set_inf(acc);
+#pragma unroll 1
+  for (int i = L - 1; i >= 0; i--) {
+    const G1Xyzz b = B[i];
+    qxyzz_add(q, run, run, b);
+    qxyzz_add(q, acc, acc, run);
+  }
+  if (ch > 0) {
+    G1Xyzz s;
+    qxyzz_mul_small(q, s, run, (uint32_t)ch * (uint32_t)L);
+    qxyzz_add(q, acc, acc, s);
+  }
+  if (q.lane == 0) out[t] = acc;
+}
+
+__global__ void __launch_bounds__(128)
+k_big_sum_quad(const G1Xyzz* __restrict__ in, int pin, int G, int pout, int total_out, G1Xyzz* __restrict__ out) {
+  const Quad q;
+  int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+  if (t >= total_out) return;
+  const int j = t / pout, g = t - j * pout;
+  int lo = g * G, hi = lo + G < pin ? lo + G : pin;
+  G1Xyzz acc;
+  xyzz_set_inf(acc);
+#pragma unroll 1
+  for (int i = lo; i < hi; i++) {
+    const G1Xyzz p = in[(size_t)j * pin + i];
+    qxyzz_add(q, acc, acc, p);
+  }
+  if (q.lane == 0) out[t] = acc;
+}
+constexpr int kBigQuadMaxOutputs = 8192;  // below this many outputs the reductions run a quad per output
+
 // out[j*pout + g] = sum of in[j*pin + g*G .. +G)
 __global__ void __launch_bounds__(128, 3)
 k_big_sum(const G1Xyzz* __restrict__ in, int pin, int G, int pout, int total_out, G1Xyzz* __restrict__ out) {
@@ -456,11 +514,11 @@ __global__ void k_big_combine(const G1Jac* __restrict__ in, int n, G1Jac* __rest
 }
 
 // ---------------------------------------------------------------- host side
-// window width by size, measured on B200 (tools/msm_sweep.py --scan-c, profiles/)
+// window width by size, measured on B200 (tools/msm_sweep.py --scan-c, profiles/r2_msm_window_scan.txt)
 int big_msm_pick_c(size_t n) {
   int lg = 0;
   while (((size_t)1 << (lg + 1)) <= n) lg++;
-  static const int table[] = {8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 11, 12, 12, 15, 15, 16, 16, 16, 16};
+  static const int table[] = {8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 9, 11, 12, 12, 15, 16, 16, 16, 16, 16};
   return lg <= 20 ? table[lg] : 16;
 }
 
@@ -569,13 +627,15 @@ cudaError_t launch_big_msm(const G1Affine* points, const Fr* scalars, const BigM
   int Lc = d.M < 8 ? d.M : 8;  // buckets per reduce1 thread: shorter serial chain, more threads
   int per = d.M / Lc;
   int total = d.nlocal * per;
-  k_big_reduce1<<<(total + 127) / 128, 128, 0, st>>>(buckets, d.M, Lc, total, red[0]);
+  if (total <= kBigQuadMaxOutputs) k_big_reduce1_quad<<<(4 * total + 127) / 128, 128, 0, st>>>(buckets, d.M, Lc, total, red[0]);
+  else k_big_reduce1<<<(total + 127) / 128, 128, 0, st>>>(buckets, d.M, Lc, total, red[0]);
   int cur = 0;
   while (per > 1) {
     int G = per > 256 ? 16 : (per > 16 ? 8 : per);
     int pout = (per + G - 1) / G;
     int tot = d.nlocal * pout;
-    k_big_sum<<<(tot + 127) / 128, 128, 0, st>>>(red[cur], per, G, pout, tot, red[cur ^ 1]);
+    if (tot <= kBigQuadMaxOutputs) k_big_sum_quad<<<(4 * tot + 127) / 128, 128, 0, st>>>(red[cur], per, G, pout, tot, red[cur ^ 1]);
+    else k_big_sum<<<(tot + 127) / 128, 128, 0, st>>>(red[cur], per, G, pout, tot, red[cur ^ 1]);
     cur ^= 1;
     per = pout;
   }

@@ -1,5 +1,5 @@
-"""Window-partitioned multi-GPU MSM (cdl_g1_msm_sharded): one process per GPU,
-NCCL all-gather of one partial sum per rank.  Needs >= 2 GPUs (run with
+"""Multi-GPU MSM (cdl_g1_msm_sharded), windows dealt to the ranks or points partitioned:
+one process per GPU, NCCL all-gather of one partial sum per rank.  Needs >= 2 GPUs (run with
 `gpurun --gpus 2`); skipped on a single-GPU box, where
 test_gpu_msm_big.test_window_partition_partials_add_up covers the arithmetic."""
 import importlib
@@ -13,7 +13,9 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, uid, n, q):
+def _worker(rank, world, uid, n, q, partition=""):
+    if partition:
+        os.environ["CDL_MSM_PARTITION"] = partition  # "windows" / "points": force one split (default: by window count)
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     pkg = importlib.import_module("go-curdleproofs_b200")
@@ -33,8 +35,9 @@ def _worker(rank, world, uid, n, q):
     ctx.close()
 
 
+@pytest.mark.parametrize("partition", ["windows", "points"])
 @pytest.mark.parametrize("n", [4096, 50000])
-def test_sharded_msm_two_ranks(pkg, n):
+def test_sharded_msm_two_ranks(pkg, n, partition):
     import torch
     import torch.multiprocessing as mp
 
@@ -44,7 +47,7 @@ def test_sharded_msm_two_ranks(pkg, n):
     uid = pkg.comm_unique_id()
     mpc = mp.get_context("spawn")
     q = mpc.Queue()
-    procs = [mpc.Process(target=_worker, args=(r, world, uid, n, q)) for r in range(world)]
+    procs = [mpc.Process(target=_worker, args=(r, world, uid, n, q, partition)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=600) for _ in range(world)]
