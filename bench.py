@@ -197,6 +197,10 @@ def reference_main(args):
 
 # ----------------------------------------------------------------------------- GPU arm
 class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons of one GPU DURING the timed region.  Sampled in-process through NVML
+    (nvidia_ml_py); spawning `nvidia-smi` five times a second from every rank takes the driver's global lock
+    often enough to slow the other ranks' launches (measured at 4 GPUs), so the subprocess form is only the
+    fallback and runs at 1 Hz."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -204,31 +208,60 @@ class ClockSampler(threading.Thread):
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index = index
-        self.samples = []
+        self.sm, self.mx, self.reasons, self.n = [], [], set(), 0
         self.stop_flag = threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = index
+            if vis and all(x.strip().isdigit() for x in vis.split(",")):
+                phys = int(vis.split(",")[index])
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+            self.source = "nvml"
+        except Exception:
+            self.source = "nvidia-smi"
+
+    def sample(self):
+        if self.nvml is not None:
+            nv = self.nvml
+            self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+            self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)))
+            try:
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for name, bit in (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+                              ("sw_power_cap", 0x4)):
+                if r & bit:
+                    self.reasons.add(name)
+        else:
+            out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                  str(self.index)], capture_output=True, text=True, timeout=10).stdout.strip()
+            s = [x.strip() for x in out.split(",")]
+            if len(s) > 8:
+                self.sm.append(float(s[1]))
+                self.mx.append(float(s[2]))
+                for k, nm in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+                    if s[5 + k].lower().startswith("active"):
+                        self.reasons.add(nm)
+        self.n += 1
 
     def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                self.sample()
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.2 if self.nvml is not None else 1.0)
 
     def summary(self):
-        sm = [float(s[1]) for s in self.samples if len(s) > 2 and s[1].replace(".", "").isdigit()]
-        mx = [float(s[2]) for s in self.samples if len(s) > 2 and s[2].replace(".", "").isdigit()]
-        reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
-            for k, nm in enumerate(names):
-                if len(s) > 5 + k and s[5 + k].lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.samples)}
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": self.n, "source": self.source}
 
 
 def make_trackers(ctx, pkg, ell: int, seeds):

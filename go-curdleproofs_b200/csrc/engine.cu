@@ -67,7 +67,7 @@ Engine::~Engine() {
   cudaSetDevice(ctx_->device);
   if (d_pool_) cudaFree(d_pool_);
   if (d_win_) cudaFree(d_win_);
-  for (Staging* s : {&s_idx_, &s_sc_, &s_task_, &s_out_, &s_ops_, &s_enc_, &s_st_, &s_jac_, &s_sub_, &s_t2_}) {
+  for (Staging* s : {&s_idx_, &s_sc_, &s_task_, &s_out_, &s_ops_, &s_enc_, &s_st_, &s_jac_, &s_sub_, &s_t2_, &s_cr_}) {
     if (s->h) cudaFreeHost(s->h);
     if (s->d) cudaFree(s->d);
   }
@@ -175,6 +175,22 @@ int32_t Engine::copy_points(uint32_t dst, uint32_t src, size_t count) {
 int32_t Engine::set_infinity(uint32_t dst, size_t count) {
   if (!count) return CDL_OK;
   CDL_CUDA(ctx_, cudaMemsetAsync(d_pool_ + dst, 0, count * sizeof(G1Affine), ctx_->stream));
+  return CDL_OK;
+}
+
+int32_t Engine::copy_ranges(const std::vector<cdl::CopyRange>& ranges) {
+  const size_t n = ranges.size();
+  if (!n) return CDL_OK;
+  // own staging buffer: the copy is left in flight (the next stage's launch syncs), so the pinned
+  // descriptors must not be shared with a stage that refills its staging before that sync
+  CDL_CUDA(ctx_, ctx_->sync_stream());  // a previous copy_ranges may still be reading s_cr_
+  int32_t rc = reserve(s_cr_, n * sizeof(cdl::CopyRange));
+  if (rc) return rc;
+  memcpy(s_cr_.h, ranges.data(), n * sizeof(cdl::CopyRange));
+  CDL_CUDA(ctx_, cudaMemcpyAsync(s_cr_.d, s_cr_.h, n * sizeof(cdl::CopyRange), cudaMemcpyHostToDevice, ctx_->stream));
+  cdl::launch_copy_ranges(d_pool_, (const cdl::CopyRange*)s_cr_.d, (int)n, ctx_->stream);
+  CDL_CUDA(ctx_, cudaGetLastError());
+  launches++;
   return CDL_OK;
 }
 
@@ -592,8 +608,9 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
         ops[b * n + ell + j] = ElemOp{L.Hs + j, cdl::kNoPoint, base + L.Gp + ell + j, (uint32_t)(b * (ell + 1) + ell)};
     });
     if ((rc = run_elem(ops, sc))) return rc;
-    for (uint32_t b = 0; b < B; b++)
-      if ((rc = copy_points(L.base(b) + L.G, L.Gs, n))) return rc;  // Gs and Hs are adjacent in the CRS image
+    std::vector<cdl::CopyRange> cr(B);
+    for (uint32_t b = 0; b < B; b++) cr[b] = cdl::CopyRange{L.Gs, L.base(b) + L.G, n, 0};  // Gs and Hs are adjacent in the CRS image
+    if ((rc = copy_ranges(cr))) return rc;
   }
   // D, the self-check on D, B_c, B_d  (:105-177, innerproductargument.go:59-72).
   // D = B - <beta^i, Gs'> + <alpha*beta^(ell+1), Hs'> (:132-138) with Gs'[i] = beta^-(i+1) Gs[i] and
@@ -743,16 +760,22 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
     const uint32_t terms = (split ? 2 * ell : 6 * (ell + 1)) + 4 + 3 + (n) + (ell + 1) + (ell + 1);
     StageBuilder sb(st, B, terms, 14);
     // working vectors of the same-multiscalar argument
-    for (uint32_t b = 0; b < B; b++) {
-      uint32_t base = L.base(b);
-      if ((rc = copy_points(base + L.Gm, L.Gs, ell + 2))) return rc;       // Gs || Hs[0..2)
-      if ((rc = copy_points(base + L.Gm + ell + 2, L.Gt, 2))) return rc;   // Gt, Gu
-      if ((rc = copy_points(base + L.Tp, base + L.Ts, ell))) return rc;
-      if ((rc = copy_points(base + L.Up, base + L.Us, ell))) return rc;
-      if ((rc = set_infinity(base + L.Tp + ell, 4))) return rc;
-      if ((rc = set_infinity(base + L.Up + ell, 4))) return rc;
-      if ((rc = copy_points(base + L.Tp + ell + 2, L.H, 1))) return rc;    // T' = Ts || 0 || 0 || H || 0
-      if ((rc = copy_points(base + L.Up + ell + 3, L.H, 1))) return rc;    // U' = Us || 0 || 0 || 0 || H
+    {
+      std::vector<cdl::CopyRange> cr;
+      cr.reserve((size_t)B * 8);
+      for (uint32_t b = 0; b < B; b++) {
+        uint32_t base = L.base(b);
+        cr.push_back({L.Gs, base + L.Gm, ell + 2, 0});                 // Gs || Hs[0..2)
+        cr.push_back({L.Gt, base + L.Gm + ell + 2, 2, 0});             // Gt, Gu
+        cr.push_back({base + L.Ts, base + L.Tp, ell, 0});
+        cr.push_back({base + L.Us, base + L.Up, ell, 0});
+        cr.push_back({cdl::kNoPoint, base + L.Tp + ell, 2, 0});        // T' = Ts || 0 || 0 || H || 0
+        cr.push_back({L.H, base + L.Tp + ell + 2, 1, 0});
+        cr.push_back({cdl::kNoPoint, base + L.Tp + ell + 3, 1, 0});
+        cr.push_back({cdl::kNoPoint, base + L.Up + ell, 3, 0});        // U' = Us || 0 || 0 || 0 || H
+        cr.push_back({L.H, base + L.Up + ell + 3, 1, 0});
+      }
+      if ((rc = copy_ranges(cr))) return rc;
     }
     par(B, [&](size_t b) {
       ProveState& s = *S[b];

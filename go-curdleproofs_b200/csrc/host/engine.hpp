@@ -124,6 +124,7 @@ class Engine {
   int32_t download_points(uint32_t src, void* host_affine, size_t count);
   int32_t copy_points(uint32_t dst, uint32_t src, size_t count);
   int32_t set_infinity(uint32_t dst, size_t count);
+  int32_t copy_ranges(const std::vector<cdl::CopyRange>& ranges);  // many pool-to-pool copies in one launch
   int32_t compress(const std::vector<uint32_t>& src, std::vector<uint8_t>& out48);
   int32_t decompress(const uint8_t* enc48, const std::vector<uint32_t>& dst, std::vector<uint8_t>& status);
   int32_t run_msm(MsmStage& st);
@@ -184,7 +185,7 @@ class Engine {
     void* d = nullptr;
     size_t cap = 0;
   };
-  Staging s_idx_, s_sc_, s_task_, s_out_, s_ops_, s_enc_, s_st_, s_jac_, s_sub_, s_t2_;
+  Staging s_idx_, s_sc_, s_task_, s_out_, s_ops_, s_enc_, s_st_, s_jac_, s_sub_, s_t2_, s_cr_;
   int32_t reserve(Staging& s, size_t bytes);
   void tick();                                   // event before a kernel
   void tock(int cls, double modmul, double bytes);  // event after; call finish_timing() after the sync

@@ -255,6 +255,26 @@ void launch_scalar_mul(const G1Affine* P, const Fr* s, int stride, const G1Affin
   if (!resident) resident = resident_ctas(k_scalar_mul, tpb);
   k_scalar_mul<<<balanced_blocks(n, tpb, resident), tpb, 0, st>>>(P, s, stride, L, out, n);
 }
+// pool[dst .. dst+count) = pool[src .. src+count) (src == kNoPoint: the point at infinity) for many ranges
+// in one launch: the working vectors of a batch (G, G', T', U' of every instance) are set up by a
+// handful of launches instead of thousands of tiny device-to-device copies.
+__global__ void __launch_bounds__(128)
+k_copy_ranges(G1Affine* __restrict__ pool, const CopyRange* __restrict__ ranges, int n) {
+  const CopyRange r = ranges[blockIdx.x];
+  uint4* d = reinterpret_cast<uint4*>(pool + r.dst);
+  const int granules = (int)r.count * (int)(sizeof(G1Affine) / 16);
+  if (r.src == kNoPoint) {
+    for (int i = threadIdx.x; i < granules; i += blockDim.x) d[i] = make_uint4(0, 0, 0, 0);
+  } else {
+    const uint4* s = reinterpret_cast<const uint4*>(pool + r.src);
+    for (int i = threadIdx.x; i < granules; i += blockDim.x) d[i] = s[i];
+  }
+  (void)n;
+}
+void launch_copy_ranges(G1Affine* pool, const CopyRange* ranges, int n, cudaStream_t st) {
+  if (n > 0) k_copy_ranges<<<n, 128, 0, st>>>(pool, ranges, n);
+}
+
 void launch_jac_to_affine(const G1Jac* in, G1Affine* out, int n, cudaStream_t st) {
   if (n <= 0) return;
   if (n >= 8 * 148 * 64) {

@@ -20,6 +20,11 @@ struct ElemOp {
   uint32_t src, add, dst, sc;
 };
 constexpr uint32_t kNoPoint = 0xffffffffu;
+// pool[dst .. dst+count) = pool[src .. src+count); src == kNoPoint fills with the point at infinity.
+// Ranges of one launch must not overlap each other's destinations.
+struct CopyRange {
+  uint32_t src, dst, count, pad;
+};
 constexpr size_t kMsmMaxSmem = 220 * 1024;         // dynamic shared memory opt-in for the small-MSM kernel
 constexpr size_t kMsmMaxTerms = kMsmMaxSmem / 36;  // 36 B of staging per term
 
@@ -31,6 +36,7 @@ void launch_scalar_mul(const G1Affine* P, const Fr* s, int stride, const G1Affin
                        cudaStream_t st);
 void launch_jac_to_affine(const G1Jac* in, G1Affine* out, int n, cudaStream_t st);
 void launch_elem_ops(G1Affine* pool, const ElemOp* ops, const Fr* scalars, int n, cudaStream_t st);
+void launch_copy_ranges(G1Affine* pool, const CopyRange* ranges, int n, cudaStream_t st);
 // indexed codecs on a pool: enc[i] <- pool[src[i]] ; pool[dst[i]] <- enc[i]
 void launch_compress_idx(const G1Affine* pool, const uint32_t* src, uint8_t* out48, int n, cudaStream_t s);
 void launch_decompress_idx(const uint8_t* in48, G1Affine* pool, const uint32_t* dst, uint8_t* status, int n,
