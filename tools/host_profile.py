@@ -4,6 +4,7 @@ prints one line per lane engine when the context closes).  Usage:
   [taskset -c 0-3] python tools/host_profile.py [B] [lanes] [passes]"""
 import importlib
 import os
+import resource
 import sys
 import time
 
@@ -26,17 +27,29 @@ sets = bench.make_trackers(ctx, pkg, bench.ELL, [1000 + i for i in range(4)])
 pre = b"".join(sets[i % 4] for i in range(B))
 rg = [[pkg.Rand((p << 20) | i) for i in range(B)] for p in range(passes + 1)]
 rv = [[pkg.Rand((1 << 30) | (p << 20) | i) for i in range(B)] for p in range(passes + 1)]
-tg, tv = [], []
+def cpu_s():
+    r = resource.getrusage(resource.RUSAGE_SELF)
+    return r.ru_utime + r.ru_stime
+
+
+tg, tv, cg, cv = [], [], [], []
 for p in range(passes + 1):
+    c0 = cpu_s()
     t0 = time.perf_counter()
     post, proofs, st = ctx.whisk_generate_shuffle_proof_batch(crs, pre, rg[p])
     t1 = time.perf_counter()
+    c1 = cpu_s()
     ok, vs = ctxv.whisk_is_valid_shuffle_proof_batch(crsv, pre, post, proofs, rv[p])
     t2 = time.perf_counter()
+    c2 = cpu_s()
     assert st == [0] * B and ok == [1] * B
     if p:
         tg.append(t1 - t0)
         tv.append(t2 - t1)
+        cg.append(c1 - c0)
+        cv.append(c2 - c1)
+print(f"host CPU (user + sys, all threads) per proof: generate {1e3 * sum(cg) / len(cg) / B:.3f} ms, "
+      f"validate {1e3 * sum(cv) / len(cv) / B:.3f} ms")
 print(f"cores {len(os.sched_getaffinity(0))} B {B} lanes {lanes}: generate {B / (sum(tg) / len(tg)):.0f} proofs/s, "
       f"validate {B / (sum(tv) / len(tv)):.0f} /s, round trip {B / ((sum(tg) + sum(tv)) / len(tg)):.0f} /s")
 sys.stdout.flush()

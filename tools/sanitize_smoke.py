@@ -34,3 +34,14 @@ post, proofs, status = ctx.whisk_generate_shuffle_proof_batch(crs, pre, [pkg.Ran
 ok, st = ctx.whisk_is_valid_shuffle_proof_batch(crs, pre, post, proofs, [pkg.Rand(2000 + i) for i in range(B)])
 assert status == [0] * B and ok == [1] * B and st == [0] * B
 print("sanitize smoke ok")
+# one proof at a time: the quad (warp-cooperative) kernels, the small-MSM CTA kernel and the few-task Horner
+post1, proof1 = ctx.whisk_generate_shuffle_proof(crs, pre[:ell * 96], pkg.Rand(7))
+assert ctx.whisk_is_valid_shuffle_proof(crs, pre[:ell * 96], post1, proof1, pkg.Rand(8)) is True
+# device-resident pool MSM and the persistent elementwise kernel above its quad threshold
+pool = ctx.dev_buffer(96 * (n + 2))
+pool.upload(pts + bytes(192))
+aff, enc48 = ctx.g1_msm_batch_device(pool, list(range(64)) * 2, pkg.Rand(9).get_frs(128), [0, 64, 128], out_slot=[n, n + 1])
+big = 9000
+pts2 = ctx.g1_scalar_mul_affine((pts * 3)[:96 * big], pkg.Rand(10).get_frs(big), broadcast=False)
+assert len(pts2) == 96 * big and len(aff) == 192 and len(enc48) == 96
+print("sanitize smoke 2 ok")
