@@ -67,7 +67,7 @@ Engine::~Engine() {
   cudaSetDevice(ctx_->device);
   if (d_pool_) cudaFree(d_pool_);
   if (d_win_) cudaFree(d_win_);
-  for (Staging* s : {&s_idx_, &s_sc_, &s_task_, &s_out_, &s_ops_, &s_enc_, &s_st_, &s_jac_, &s_sub_, &s_t2_, &s_cr_}) {
+  for (Staging* s : {&s_idx_, &s_sc_, &s_task_, &s_out_, &s_ops_, &s_enc_, &s_st_, &s_jac_, &s_sub_, &s_t2_, &s_cr_, &s_vs_, &s_as_}) {
     if (s->h) cudaFreeHost(s->h);
     if (s->d) cudaFree(s->d);
   }
@@ -246,7 +246,7 @@ int32_t Engine::decompress(const uint8_t* enc48, const std::vector<uint32_t>& ds
   return CDL_OK;
 }
 
-int32_t Engine::run_msm(MsmStage& st) {
+int32_t Engine::run_msm(MsmStage& st, const std::function<int32_t(cdl::Fr* d_scalars)>& before) {
   ProfScope ps(prof.gpu);
   size_t nt = st.tasks.size(), nterm = st.idx.size();
   st.out48.resize(nt * 48);
@@ -266,6 +266,10 @@ int32_t Engine::run_msm(MsmStage& st) {
   CDL_CUDA(ctx_, cudaMemcpyAsync(s_idx_.d, s_idx_.h, nterm * 4, cudaMemcpyHostToDevice, ctx_->stream));
   CDL_CUDA(ctx_, cudaMemcpyAsync(s_sc_.d, s_sc_.h, nterm * 32, cudaMemcpyHostToDevice, ctx_->stream));
   CDL_CUDA(ctx_, cudaMemcpyAsync(s_task_.d, s_task_.h, nt * sizeof(MsmTask), cudaMemcpyHostToDevice, ctx_->stream));
+  if (before) {
+    int32_t brc = before((cdl::Fr*)s_sc_.d);
+    if (brc) return brc;
+  }
   double alg = 0;
   for (auto& t : st.tasks) alg += msm_algorithmic_modmul(t.term_cnt);
   if ((int)nt >= cdl::kMsmSplitThreshold || max_terms > cdl::kMsmSplitTerms) {
@@ -349,11 +353,6 @@ struct StageBuilder {
     s.tasks = st.tasks.data() + (size_t)b * tasks_per;
     s.term_base = b * terms_per;
     return s;
-  }
-  // unused tail terms/tasks of an instance stay zero-length; compact before running
-  void compact() {
-    // tasks with term_cnt == 0 and out_idx == 0 that were never begun are dropped only when a
-    // whole instance was skipped (error state); keep the layout otherwise.
   }
   const uint8_t* out(uint32_t b, uint32_t task) const { return st.out48.data() + ((size_t)b * tasks_per + task) * 48; }
 };

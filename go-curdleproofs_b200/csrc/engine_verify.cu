@@ -150,6 +150,15 @@ int32_t Engine::verify(const Layout& L, uint32_t B, const cdl_crs* crs, std::vec
   std::vector<std::vector<Fr>> t_sc(B);
   std::vector<std::vector<uint32_t>> t_cnt(B);  // term count of each of the instance's tasks
   std::vector<uint8_t> have_big(B, 0);
+  // The scalars of the 5*ell + 7 structurally shared bases are computed on the device from a small per-proof
+  // block (k_verify_scalars.cu); CDL_VERIFY_SCALARS=host keeps the host computation (cross-check, A/B).
+  static const bool device_scalars = [] {
+    const char* e = getenv("CDL_VERIFY_SCALARS");
+    return !(e && e[0] == 'h');
+  }();
+  const bool dev_sc = device_scalars && L.m <= (uint32_t)cdl::kVsMaxM;
+  std::vector<cdl::VsParams> vsp(dev_sc ? B : 0);
+  std::vector<uint32_t> merged_at(B, 0);  // position of the first merged-base term inside the instance's big task
   par(B, [&](size_t b) {
     VState& s = *S[b];
     if (s.failed) return;
@@ -168,17 +177,16 @@ int32_t Engine::verify(const Layout& L, uint32_t B, const cdl_crs* crs, std::vec
 
     // -- same-permutation: C = B - A - alpha*M ; <beta.., Gs>   (samepermutationargument.go:132-142)
     Fr a1 = rand.get_fr();
-    {
-      const Fr a1b = fr_mul(a1, s.sp_beta);
+    const Fr a1b = fr_mul(a1, s.sp_beta);
+    if (!dev_sc)
       for (uint32_t i = 0; i < ell; i++) sGs[i] = a1b;
-    }
     neg_term(q.pt[w.B], a1);
     neg_term(q.pt[w.A], fr_neg(a1));
     neg_term(q.pt[w.M], fr_neg(fr_mul(a1, s.sp_alpha)));
 
     // -- grand product -> inner product (grandproductargument.go:234-283, innerproductargument.go:201-294)
-    std::vector<Fr> us(n);
-    {
+    std::vector<Fr> us(dev_sc ? 0 : n);
+    if (!dev_sc) {
       Fr t = s.gp_beta_inv;
       for (uint32_t i = 0; i < ell; i++) { us[i] = t; t = fr_mul(t, s.gp_beta_inv); }
       for (uint32_t i = ell; i < n; i++) us[i] = t;
@@ -210,18 +218,22 @@ int32_t Engine::verify(const Layout& L, uint32_t B, const cdl_crs* crs, std::vec
     std::vector<Fr> gamma_inv = fr_batch_inv(gamma);
     // s[i] = prod over the set bits j of i of gamma[m-j-1] (innerproductargument.go:223-234), built by
     // doubling: one product per entry instead of one per set bit
-    std::vector<Fr> sv(n), svp(n);
-    sv[0] = svp[0] = FR_ONE;
-    for (uint32_t j = 0; j < m; j++)
-      for (uint32_t i = 0; i < (1u << j); i++) {
-        sv[i + (1u << j)] = fr_mul(sv[i], gamma[m - j - 1]);
-        svp[i + (1u << j)] = fr_mul(svp[i], gamma_inv[m - j - 1]);
-      }
+    std::vector<Fr> sv(dev_sc ? 0 : n), svp(dev_sc ? 0 : n);
+    if (!dev_sc) {
+      sv[0] = svp[0] = FR_ONE;
+      for (uint32_t j = 0; j < m; j++)
+        for (uint32_t i = 0; i < (1u << j); i++) {
+          sv[i + (1u << j)] = fr_mul(sv[i], gamma[m - j - 1]);
+          svp[i + (1u << j)] = fr_mul(svp[i], gamma_inv[m - j - 1]);
+        }
+    }
     // AC1 = <gamma, L_C> + B_c + alpha*C + (alpha^2 z)*(beta*H) + <gamma^-1, R_C>  vs  c0*s on Gs||Hs, beta*d0*c0 on H
     Fr a2 = rand.get_fr();
     const Fr a2c0 = fr_mul(a2, c0);
-    for (uint32_t i = 0; i < ell; i++) sGs[i] = fr_add(sGs[i], fr_mul(a2c0, sv[i]));
-    for (uint32_t j = 0; j < 4; j++) sHs[j] = fr_add(sHs[j], fr_mul(a2c0, sv[ell + j]));
+    if (!dev_sc) {
+      for (uint32_t i = 0; i < ell; i++) sGs[i] = fr_add(sGs[i], fr_mul(a2c0, sv[i]));
+      for (uint32_t j = 0; j < 4; j++) sHs[j] = fr_add(sHs[j], fr_mul(a2c0, sv[ell + j]));
+    }
     sH = fr_add(sH, fr_mul(a2, fr_mul(fr_mul(ipa_beta, d0), c0)));
     for (uint32_t i = 0; i < m; i++) {
       neg_term(q.pt[w.L_C + i], fr_mul(a2, gamma[i]));
@@ -233,8 +245,10 @@ int32_t Engine::verify(const Layout& L, uint32_t B, const cdl_crs* crs, std::vec
     // AC2 = <gamma, L_D> + B_d + alpha*D + <gamma^-1, R_D>  vs  s'*us*d0 on Gs||Hs;  D = B - beta^-1 Gsum + alpha_gp Hsum
     Fr a3 = rand.get_fr();
     const Fr a3d0 = fr_mul(a3, d0);
-    for (uint32_t i = 0; i < ell; i++) sGs[i] = fr_add(sGs[i], fr_mul(a3d0, fr_mul(svp[i], us[i])));
-    for (uint32_t j = 0; j < 4; j++) sHs[j] = fr_add(sHs[j], fr_mul(a3d0, fr_mul(svp[ell + j], us[ell + j])));
+    if (!dev_sc) {
+      for (uint32_t i = 0; i < ell; i++) sGs[i] = fr_add(sGs[i], fr_mul(a3d0, fr_mul(svp[i], us[i])));
+      for (uint32_t j = 0; j < 4; j++) sHs[j] = fr_add(sHs[j], fr_mul(a3d0, fr_mul(svp[ell + j], us[ell + j])));
+    }
     for (uint32_t i = 0; i < m; i++) {
       neg_term(q.pt[w.L_D + i], fr_mul(a3, gamma[i]));
       neg_term(q.pt[w.R_D + i], fr_mul(a3, gamma_inv[i]));
@@ -299,17 +313,21 @@ int32_t Engine::verify(const Layout& L, uint32_t B, const cdl_crs* crs, std::vec
       }
       std::vector<Fr> ch_inv = fr_batch_inv(ch);
       // xs[i] = x * prod over the set bits j of i of ch[lg_n-1-j] (samemultiscalarargument.go:267-277), by doubling
-      std::vector<Fr> xs(n);
-      xs[0] = xf;
-      for (uint32_t j = 0; j < lg_n; j++)
-        for (uint32_t i = 0; i < (1u << j); i++) xs[i + (1u << j)] = fr_mul(xs[i], ch[lg_n - 1 - j]);
+      std::vector<Fr> xs(dev_sc ? 0 : n);
+      if (!dev_sc) {
+        xs[0] = xf;
+        for (uint32_t j = 0; j < lg_n; j++)
+          for (uint32_t i = 0; i < (1u << j); i++) xs[i + (1u << j)] = fr_mul(xs[i], ch[lg_n - 1 - j]);
+      }
       // over G = Gs || Hs[0..2) || Gt || Gu with point B_a + alpha*A' + <ch, L_A> + <ch^-1, R_A>
       Fr a4 = rand.get_fr();
-      for (uint32_t i = 0; i < ell; i++) sGs[i] = fr_add(sGs[i], fr_mul(a4, xs[i]));
-      sHs[0] = fr_add(sHs[0], fr_mul(a4, xs[ell]));
-      sHs[1] = fr_add(sHs[1], fr_mul(a4, xs[ell + 1]));
-      sGt = fr_add(sGt, fr_mul(a4, xs[ell + 2]));
-      sGu = fr_add(sGu, fr_mul(a4, xs[ell + 3]));
+      if (!dev_sc) {
+        for (uint32_t i = 0; i < ell; i++) sGs[i] = fr_add(sGs[i], fr_mul(a4, xs[i]));
+        sHs[0] = fr_add(sHs[0], fr_mul(a4, xs[ell]));
+        sHs[1] = fr_add(sHs[1], fr_mul(a4, xs[ell + 1]));
+        sGt = fr_add(sGt, fr_mul(a4, xs[ell + 2]));
+        sGu = fr_add(sGu, fr_mul(a4, xs[ell + 3]));
+      }
       neg_term(q.pt[w.B_a], a4);
       neg_term(base + L.scratch, fr_mul(a4, sm_alpha));  // A' from launch 1
       for (uint32_t i = 0; i < lg_n; i++) {
@@ -318,8 +336,10 @@ int32_t Engine::verify(const Layout& L, uint32_t B, const cdl_crs* crs, std::vec
       }
       // over T' = Ts || 0 || 0 || H || 0 with point B_t + alpha*T_2 + ...
       Fr a5 = rand.get_fr();
-      for (uint32_t i = 0; i < ell; i++) sTs[i] = fr_add(sTs[i], fr_mul(a5, xs[i]));
-      sH = fr_add(sH, fr_mul(a5, xs[ell + 2]));
+      if (!dev_sc) {
+        for (uint32_t i = 0; i < ell; i++) sTs[i] = fr_add(sTs[i], fr_mul(a5, xs[i]));
+        sH = fr_add(sH, fr_mul(a5, xs[ell + 2]));
+      }
       neg_term(q.pt[w.B_t], a5);
       neg_term(q.pt[w.T2], fr_mul(a5, sm_alpha));
       for (uint32_t i = 0; i < lg_n; i++) {
@@ -328,8 +348,10 @@ int32_t Engine::verify(const Layout& L, uint32_t B, const cdl_crs* crs, std::vec
       }
       // over U' = Us || 0 || 0 || 0 || H with point B_u + alpha*U_2 + ...
       Fr a6 = rand.get_fr();
-      for (uint32_t i = 0; i < ell; i++) sUs[i] = fr_add(sUs[i], fr_mul(a6, xs[i]));
-      sH = fr_add(sH, fr_mul(a6, xs[ell + 3]));
+      if (!dev_sc) {
+        for (uint32_t i = 0; i < ell; i++) sUs[i] = fr_add(sUs[i], fr_mul(a6, xs[i]));
+        sH = fr_add(sH, fr_mul(a6, xs[ell + 3]));
+      }
       neg_term(q.pt[w.B_u], a6);
       neg_term(q.pt[w.U2], fr_mul(a6, sm_alpha));
       for (uint32_t i = 0; i < lg_n; i++) {
@@ -338,11 +360,25 @@ int32_t Engine::verify(const Layout& L, uint32_t B, const cdl_crs* crs, std::vec
       }
       // R == <as, Rs>, S == <as, Ss>   (curdleproof.go:306-311)
       Fr a7 = rand.get_fr();
-      for (uint32_t i = 0; i < ell; i++) sRs[i] = fr_mul(a7, s.as[i]);
+      if (!dev_sc)
+        for (uint32_t i = 0; i < ell; i++) sRs[i] = fr_mul(a7, s.as[i]);
       neg_term(q.pt[w.R], a7);
       Fr a8 = rand.get_fr();
-      for (uint32_t i = 0; i < ell; i++) sSs[i] = fr_mul(a8, s.as[i]);
+      if (!dev_sc)
+        for (uint32_t i = 0; i < ell; i++) sSs[i] = fr_mul(a8, s.as[i]);
       neg_term(q.pt[w.S], a8);
+      if (dev_sc) {  // the inputs of k_verify_scalars; sH holds the host part of H's scalar at this point
+        cdl::VsParams& P = vsp[b];
+        auto put = [](cdl::Fr& d, const Fr& v) { memcpy(&d, &v, 32); };
+        put(P.a1b, a1b); put(P.a2c0, a2c0); put(P.a3d0, a3d0);
+        put(P.a4xf, fr_mul(a4, xf)); put(P.a5xf, fr_mul(a5, xf)); put(P.a6xf, fr_mul(a6, xf));
+        put(P.a7, a7); put(P.a8, a8); put(P.beta_inv, s.gp_beta_inv); put(P.sH_host, sH);
+        for (uint32_t i = 0; i < m; i++) { put(P.gamma[i], gamma[i]); put(P.gamma_inv[i], gamma_inv[i]); put(P.ch[i], ch[i]); }
+        P.sc_base = 0;  // set when the stage is assembled
+        P.as_base = (uint32_t)(b * ell);
+        P.pad[0] = P.pad[1] = 0;
+      }
+      merged_at[b] = (uint32_t)idx.size();
       // the merged bases
       for (uint32_t i = 0; i < ell; i++) { idx.push_back(L.Gs + i); sc.push_back(sGs[i]); }
       for (uint32_t j = 0; j < 4; j++) { idx.push_back(L.Hs + j); sc.push_back(sHs[j]); }
@@ -371,12 +407,20 @@ int32_t Engine::verify(const Layout& L, uint32_t B, const cdl_crs* crs, std::vec
   // ---- launch 2: the four same-scalar equalities + the collapsed accumulator per proof
   st.clear();
   std::vector<int> first_task(B, -1);
+  std::vector<cdl::VsParams> vs_launch;
+  vs_launch.reserve(dev_sc ? B : 0);
   for (uint32_t b = 0; b < B; b++) {
     if (S[b]->failed) continue;
     first_task[b] = (int)st.tasks.size();
     uint32_t off = (uint32_t)st.idx.size();
     st.idx.insert(st.idx.end(), t_idx[b].begin(), t_idx[b].end());
     st.sc.insert(st.sc.end(), t_sc[b].begin(), t_sc[b].end());
+    if (dev_sc && have_big[b]) {  // small tasks (14 terms) come first in the slice, then the big task
+      uint32_t small_terms = 0;
+      for (size_t t = 0; t + 1 < t_cnt[b].size(); t++) small_terms += t_cnt[b][t];
+      vsp[b].sc_base = off + small_terms + merged_at[b];
+      vs_launch.push_back(vsp[b]);
+    }
     uint32_t k = 0;
     for (uint32_t cnt : t_cnt[b]) {
       st.tasks.push_back(MsmTask{off, cnt, L.base(b) + L.scratch + 2 + k, 0});
@@ -384,7 +428,28 @@ int32_t Engine::verify(const Layout& L, uint32_t B, const cdl_crs* crs, std::vec
       k++;
     }
   }
-  if ((rc = run_msm(st))) return rc;
+  if (dev_sc && !vs_launch.empty()) {
+    // per-proof parameter blocks and the vector challenges `as` go up once; the kernel runs on the stream
+    // between the stage's uploads and its MSM kernels
+    const size_t np = vs_launch.size();
+    if ((rc = reserve(s_vs_, np * sizeof(cdl::VsParams))) || (rc = reserve(s_as_, (size_t)B * ell * 32))) return rc;
+    memcpy(s_vs_.h, vs_launch.data(), np * sizeof(cdl::VsParams));
+    Fr* as_h = (Fr*)s_as_.h;
+    par(B, [&](size_t b) {
+      if (have_big[b]) memcpy(as_h + b * ell, S[b]->as.data(), (size_t)ell * 32);
+    });
+    CDL_CUDA(ctx_, cudaMemcpyAsync(s_vs_.d, s_vs_.h, np * sizeof(cdl::VsParams), cudaMemcpyHostToDevice, ctx_->stream));
+    CDL_CUDA(ctx_, cudaMemcpyAsync(s_as_.d, s_as_.h, (size_t)B * ell * 32, cudaMemcpyHostToDevice, ctx_->stream));
+    rc = run_msm(st, [&](cdl::Fr* d_sc) -> int32_t {
+      cdl::launch_verify_scalars((const cdl::VsParams*)s_vs_.d, (const cdl::Fr*)s_as_.d, d_sc, (uint32_t)np, ell, n, L.m,
+                                 ctx_->stream);
+      launches++;
+      return CDL_OK;
+    });
+  } else {
+    rc = run_msm(st);
+  }
+  if (rc) return rc;
   for (uint32_t b = 0; b < B; b++) {
     VState& s = *S[b];
     if (s.failed) { status[b] = CDL_ERR_PROTOCOL; errs[b] = s.err; continue; }

@@ -57,7 +57,6 @@ using Fp = FpM::El;  // 48 bytes == gnark fp.Element
 using Fr = FrM::El;  // 32 bytes == gnark fr.Element
 
 // public exponents, little-endian 32-bit words
-#define CDL_FP_PM2   {0xffffaaa9u, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u, 0xf38512bfu, 0x64774b84u, 0x434bacd7u, 0x4b1ba7b6u, 0x397fe69au, 0x1a0111eau}
 // (p+1)/4
 #define CDL_FP_SQRT  {0xffffeaabu, 0xee7fbfffu, 0xac54ffffu, 0x07aaffffu, 0x3dac3d89u, 0xd9cc34a8u, 0x3ce144afu, 0xd91dd2e1u, 0x90d2eb35u, 0x92c6e9edu, 0x8e5ff9a6u, 0x0680447au}
 // (p-1)/2
@@ -67,22 +66,16 @@ using Fr = FrM::El;  // 32 bytes == gnark fr.Element
 #define CDL_FP_B     {0x000cfff3u, 0xaa270000u, 0xfc34000au, 0x53cc0032u, 0x6b0a807fu, 0x478fe97au, 0xe6ba24d7u, 0xb1d37ebeu, 0xbf78ab2fu, 0x8ec9733bu, 0x3d83de7eu, 0x09d64551u}
 #define CDL_FP_BETA  {0x8671f071u, 0xcd03c9e4u, 0x1fcda5d2u, 0x5dab2246u, 0xd3851b95u, 0x587042afu, 0x01bacb9eu, 0x8eb60ebeu, 0x83d050d2u, 0x03f97d6eu, 0x54638741u, 0x18f02065u}
 
-static const uint32_t FP_PM2_H[12] = CDL_FP_PM2;
 static const uint32_t FP_SQRT_H[12] = CDL_FP_SQRT;
 static const uint32_t FP_HALF_H[12] = CDL_FP_HALF;
 static const uint32_t FP_B_H[12] = CDL_FP_B;
 static const uint32_t FP_BETA_H[12] = CDL_FP_BETA;
 #if defined(__CUDACC__)
-static __device__ __constant__ uint32_t FP_PM2_D[12] = CDL_FP_PM2;
 static __device__ __constant__ uint32_t FP_SQRT_D[12] = CDL_FP_SQRT;
 static __device__ __constant__ uint32_t FP_HALF_D[12] = CDL_FP_HALF;
 static __device__ __constant__ uint32_t FP_B_D[12] = CDL_FP_B;
 static __device__ __constant__ uint32_t FP_BETA_D[12] = CDL_FP_BETA;
 #endif
-
-CDL_FN void fp_inv_fermat(Fp& r, const Fp& a) {  // a^(p-2); inv(0) = 0
-  FpM::pow_words<12>(r, a, CDL_SEL(FP_PM2_D, FP_PM2_H));
-}
 
 // Reference inversion (kept for the cross-check of fp_inv on the CPU tier): binary extended Euclid in a branch-free,
 // fixed-length form: the invariants u = x1*A, v = x2*A (mod p) hold for the raw limbs A = a*R; a

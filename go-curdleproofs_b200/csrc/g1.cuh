@@ -316,7 +316,8 @@ CDL_HD void recode_w4(int8_t* digits, const uint32_t* k) {
   }
 }
 
-// r = k * p, k canonical (non-Montgomery) little-endian words, k < 2^255.
+// r = k * p, k canonical (non-Montgomery) little-endian words, k < 2^255.  Plain signed-window form without
+// the GLV split: the CPU tier (tests/hostcheck) uses it as the independent cross-check of jac_scalar_mul_glv.
 CDL_FN void jac_scalar_mul(G1Jac& r, const G1Affine& p, const uint32_t* k) {
   if (aff_is_inf(p)) { jac_set_inf(r); return; }
   G1Jac tab[8];  // tab[i] = (i+1) p

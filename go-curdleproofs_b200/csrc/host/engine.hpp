@@ -11,6 +11,7 @@
 // the host.
 #pragma once
 #include <cstdint>
+#include <functional>
 #include <memory>
 #include <string>
 #include <vector>
@@ -127,7 +128,9 @@ class Engine {
   int32_t copy_ranges(const std::vector<cdl::CopyRange>& ranges);  // many pool-to-pool copies in one launch
   int32_t compress(const std::vector<uint32_t>& src, std::vector<uint8_t>& out48);
   int32_t decompress(const uint8_t* enc48, const std::vector<uint32_t>& dst, std::vector<uint8_t>& status);
-  int32_t run_msm(MsmStage& st);
+  // `before` (optional) runs on the stream after the stage's indices / scalars reached the device and before
+  // the MSM kernels: the verifier's scalar pipeline fills part of the scalar array there (d_scalars)
+  int32_t run_msm(MsmStage& st, const std::function<int32_t(cdl::Fr* d_scalars)>& before = nullptr);
   int32_t run_elem(const std::vector<cdl::ElemOp>& ops, const std::vector<Fr>& sc);
 
   cdl_ctx* ctx() { return ctx_; }
@@ -185,7 +188,7 @@ class Engine {
     void* d = nullptr;
     size_t cap = 0;
   };
-  Staging s_idx_, s_sc_, s_task_, s_out_, s_ops_, s_enc_, s_st_, s_jac_, s_sub_, s_t2_, s_cr_;
+  Staging s_idx_, s_sc_, s_task_, s_out_, s_ops_, s_enc_, s_st_, s_jac_, s_sub_, s_t2_, s_cr_, s_vs_, s_as_;
   int32_t reserve(Staging& s, size_t bytes);
   void tick();                                   // event before a kernel
   void tock(int cls, double modmul, double bytes);  // event after; call finish_timing() after the sync

@@ -37,6 +37,17 @@ void launch_scalar_mul(const G1Affine* P, const Fr* s, int stride, const G1Affin
 void launch_jac_to_affine(const G1Jac* in, G1Affine* out, int n, cudaStream_t st);
 void launch_elem_ops(G1Affine* pool, const ElemOp* ops, const Fr* scalars, int n, cudaStream_t st);
 void launch_copy_ranges(G1Affine* pool, const CopyRange* ranges, int n, cudaStream_t st);
+// verifier scalar pipeline on the device (k_verify_scalars.cu): per-proof inputs, all Montgomery fr.Element
+constexpr int kVsMaxM = 16;  // rounds (n <= 2^16)
+struct VsParams {
+  Fr a1b, a2c0, a3d0, a4xf, a5xf, a6xf, a7, a8, beta_inv, sH_host;
+  Fr gamma[kVsMaxM], gamma_inv[kVsMaxM], ch[kVsMaxM];
+  uint32_t sc_base;  // first merged-base scalar of this proof in the stage's scalar array
+  uint32_t as_base;  // first vector challenge of this proof in the `as` array
+  uint32_t pad[2];
+};
+void launch_verify_scalars(const VsParams* params, const Fr* as, Fr* sc, uint32_t nproofs, uint32_t ell, uint32_t n,
+                           uint32_t m, cudaStream_t st);
 // indexed codecs on a pool: enc[i] <- pool[src[i]] ; pool[dst[i]] <- enc[i]
 void launch_compress_idx(const G1Affine* pool, const uint32_t* src, uint8_t* out48, int n, cudaStream_t s);
 void launch_decompress_idx(const uint8_t* in48, G1Affine* pool, const uint32_t* dst, uint8_t* status, int n,

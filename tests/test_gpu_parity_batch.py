@@ -141,3 +141,39 @@ def test_whisk_n128_batch64_five_mutation_kinds_match_oracle(ctx, pkg):
 
 def test_n256_batch_five_mutation_kinds_match_oracle(ctx, pkg):
     run_batch(ctx, pkg, 252, 20, 5056, 2, 1)
+
+
+def test_verifier_scalars_device_and_host_paths_agree(ctx, pkg):
+    """The verifier's merged-base scalars come from k_verify_scalars (device) by default; CDL_VERIFY_SCALARS=host
+    keeps the host computation.  Both must return the verdicts of this process (which the tests above pin to
+    the oracle) on a batch with every mutation kind."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    ell, B = 12, 20
+    crs = ctx.generate_crs(ell, pkg.Rand(0))
+    sets = [make_trackers(ctx, pkg, ell, 1000 + i) for i in range(3)]
+    pres = [sets[i % 3] for i in range(B)]
+    post, proofs, status = ctx.whisk_generate_shuffle_proof_batch(crs, b"".join(pres), [pkg.Rand(3000 + i) for i in range(B)])
+    assert status == [0] * B
+    tb = 96 * ell
+    posts = [bytes(post[i * tb:(i + 1) * tb]) for i in range(B)]
+    prfs = [bytes(proofs[i * 4576:(i + 1) * 4576]) for i in range(B)]
+    for i in range(0, B, 2):
+        pres[i], posts[i], prfs[i] = mutate(ctx, pkg, (i // 2) % KINDS, ell, pres[i], posts[i], prfs[i])
+    ok, st = ctx.whisk_is_valid_shuffle_proof_batch(crs, b"".join(pres), b"".join(posts), b"".join(prfs),
+                                                    [pkg.Rand(2000 + i) for i in range(B)])
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import importlib, json, sys; sys.path.insert(0, %r); pkg = importlib.import_module('go-curdleproofs_b200'); "
+        "ctx = pkg.Context(0); crs = ctx.generate_crs(%d, pkg.Rand(0)); d = json.load(sys.stdin); "
+        "ok, st = ctx.whisk_is_valid_shuffle_proof_batch(crs, bytes.fromhex(d['pre']), bytes.fromhex(d['post']), "
+        "bytes.fromhex(d['proofs']), [pkg.Rand(2000 + i) for i in range(%d)]); print(json.dumps([ok, st]))" % (root, ell, B))
+    payload = json.dumps({"pre": b"".join(pres).hex(), "post": b"".join(posts).hex(), "proofs": b"".join(prfs).hex()})
+    out = subprocess.run([sys.executable, "-c", code], input=payload, capture_output=True, text=True,
+                         env=dict(os.environ, CDL_VERIFY_SCALARS="host"), check=True).stdout
+    assert json.loads(out.strip().splitlines()[-1]) == [ok, st]
+    assert ok.count(1) == B - len(range(0, B, 2))
+    crs.close()
