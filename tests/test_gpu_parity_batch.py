@@ -177,3 +177,8 @@ def test_verifier_scalars_device_and_host_paths_agree(ctx, pkg):
     assert json.loads(out.strip().splitlines()[-1]) == [ok, st]
     assert ok.count(1) == B - len(range(0, B, 2))
     crs.close()
+
+
+def test_n512_batch_five_mutation_kinds_match_oracle(ctx, pkg):
+    """BASELINE.json names n = 512: the batched entry points at shuffled_elements = 508 (bench.py's n512 line)."""
+    run_batch(ctx, pkg, 508, 10, 5504, 2, 1)
