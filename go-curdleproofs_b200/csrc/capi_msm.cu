@@ -81,7 +81,11 @@ int pick_c(cdl_ctx* c, size_t n) {
 int32_t big_msm_on_device(cdl_ctx* c, const G1Affine* d_pts, const Fr* d_sc, size_t n, uint32_t part, uint32_t parts,
                           int normalize, G1Jac* d_out) {
   if (n >= ((size_t)1 << 30)) return c->fail(CDL_ERR_TOO_LARGE, "msm: %zu terms exceed 2^30 - 1", n);
-  BigMsmDims d = big_msm_dims(n, pick_c(c, n), (int)part, (int)parts);
+  BigMsmDims d = big_msm_dims(n, pick_c(c, n), (int)part, (int)parts, c->msm_ba_override);
+  // the batch-affine rounds keep two generations of pair sums and the prefix products (~ 100 B per
+  // sorted entry): beyond this budget the XYZZ-only path (36 B per entry less) runs instead
+  constexpr size_t kBaScratchBudget = (size_t)48 << 30;
+  if (d.R > 0 && big_msm_scratch_bytes(d) > kBaScratchBudget) d = big_msm_dims(n, d.c, (int)part, (int)parts, 0);
   // bucket counts, scan prefixes and entry offsets are 32-bit: 2 * n * (windows owned) entries must fit
   if (big_msm_entries(d) >= ((uint64_t)1 << 32))
     return c->fail(CDL_ERR_TOO_LARGE, "msm: %zu terms x %d windows exceed 2^32 - 1 sorted entries; use more ranks or a wider window",
@@ -116,6 +120,13 @@ int32_t cdl_set_msm_window(cdl_ctx* c, int32_t window_bits) {
   if (!c || window_bits < 0 || window_bits > 18 || window_bits == 1) return CDL_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> lk(c->mu);
   c->msm_c_override = window_bits;
+  return CDL_OK;
+}
+
+int32_t cdl_set_msm_batch_affine(cdl_ctx* c, int32_t rounds) {
+  if (!c || rounds < -1 || rounds > kBigMaxBaRounds) return CDL_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(c->mu);
+  c->msm_ba_override = rounds;
   return CDL_OK;
 }
 

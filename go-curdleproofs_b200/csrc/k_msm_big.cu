@@ -13,6 +13,14 @@
 //                    slot — a counting sort; order inside a bucket is irrelevant
 //   k_big_size_sort  buckets ordered by decreasing length (counting sort), so that the
 //                    32 buckets of a warp have nearly equal trip counts
+//   k_ba_fwd / k_ba_inv / k_ba_bwd
+//                    batch-affine rounds (batch_affine.cuh): every bucket's region of the sorted
+//                    entries is padded to a multiple of 2^R slots, so that for R rounds the
+//                    neighbouring slots (2k, 2k+1) of the whole array are summed pairwise as
+//                    AFFINE additions — 6 field products each, the inversions shared by
+//                    Montgomery's trick across the pairs of a thread and then across threads —
+//                    and a bucket's region simply halves.  What is left (count / 2^R points
+//                    per bucket) goes to k_big_accum.
 //   k_big_accum      thread per bucket: XYZZ mixed additions of the bucket's points
 //   k_big_slice / k_big_large_finish
 //                    buckets above kBigLargeBucket entries (degenerate inputs: all
@@ -27,7 +35,9 @@
 // its partial sum already shifted, so the exchange is one all-gather of one point
 // per rank (k_big_combine adds them).
 #define CDL_FP_MUL_CALL 1  // one shared product body: the hot loops fit the instruction caches (mont.cuh)
+#include <cstdlib>
 #include "quad.cuh"
+#include "batch_affine.cuh"
 #include "launch.h"
 
 namespace cdl {
@@ -42,6 +52,43 @@ struct BigSliceRec {
 struct BigLargeRec {
   uint32_t bucket, slice_first, slice_count, pad;
 };
+
+// Where the summands of a bucket come from: the sorted entries (a gather from [points | phi],
+// bit 31 = negate, an index beyond both tables = padding = infinity), or — after batch-affine
+// rounds — the affine pair sums of the last round, in place.
+struct BigSrc {
+  const G1Affine* points;
+  const G1Affine* phi;
+  uint32_t n;
+  const uint32_t* entries;
+  const G1Affine* direct;  // non-null: slot t holds its point
+};
+template <bool DIRECT>
+__device__ __forceinline__ G1Affine big_src_load(const BigSrc& s, uint32_t t) {
+  if (DIRECT) return s.direct[t];
+  G1Affine q;
+  const uint32_t en = s.entries[t];
+  const uint32_t pi = en & 0x7fffffffu;
+  if (pi >= 2u * s.n) {
+    aff_set_inf(q);
+    return q;
+  }
+  q = pi < s.n ? s.points[pi] : s.phi[pi - s.n];
+  if (en >> 31) FpM::neg(q.y, q.y);
+  return q;
+}
+// x coordinate only (the forward pass of a batch-affine round needs nothing else for almost every pair)
+template <bool DIRECT>
+__device__ __forceinline__ Fp big_src_load_x(const BigSrc& s, uint32_t t) {
+  if (DIRECT) return s.direct[t].x;
+  Fp x;
+  const uint32_t pi = s.entries[t] & 0x7fffffffu;
+  if (pi >= 2u * s.n) {
+    FpM::set_zero(x);
+    return x;
+  }
+  return pi < s.n ? s.points[pi].x : s.phi[pi - s.n].x;
+}
 
 // ---------------------------------------------------------------- digits
 // Every scalar is split with the GLV endomorphism, k = +-|k1| +- k2*lambda with |k1|, k2 <
@@ -128,11 +175,11 @@ k_big_digits(const Fr* __restrict__ scalars, int n, BigMsmDims dm, uint32_t* __r
 constexpr int kScanMaxIpt = 16;
 
 __global__ void __launch_bounds__(256)
-k_scan_block_sums(const uint32_t* __restrict__ in, uint32_t n, int ipt, uint32_t* __restrict__ bsum) {
+k_scan_block_sums(const uint32_t* __restrict__ in, uint32_t n, int ipt, uint32_t pad, uint32_t* __restrict__ bsum) {
   __shared__ uint32_t sh[256];
   uint32_t base = (blockIdx.x * 256u + threadIdx.x) * (uint32_t)ipt;
   uint32_t s = 0;
-  for (int k = 0; k < ipt; k++) s += (base + k < n) ? in[base + k] : 0u;
+  for (int k = 0; k < ipt; k++) s += (base + k < n) ? ((in[base + k] + pad) & ~pad) : 0u;
   sh[threadIdx.x] = s;
   __syncthreads();
   for (int st = 128; st >= 1; st >>= 1) {
@@ -171,10 +218,10 @@ k_scan_top(uint32_t* __restrict__ bsum, uint32_t nblk) {
   }
 }
 
-// offsets[i] = exclusive prefix of counts; offsets[n] = total; counts are zeroed (they
-// become the scatter cursors)
+// offsets[i] = exclusive prefix of counts (each rounded up to a multiple of pad + 1); offsets[n] =
+// total; counts are zeroed (they become the scatter cursors)
 __global__ void __launch_bounds__(256)
-k_scan_apply(uint32_t* __restrict__ counts, uint32_t n, int ipt, const uint32_t* __restrict__ bsum,
+k_scan_apply(uint32_t* __restrict__ counts, uint32_t n, int ipt, uint32_t pad, const uint32_t* __restrict__ bsum,
              uint32_t* __restrict__ offsets) {
   __shared__ uint32_t sh[256];
   uint32_t base = (blockIdx.x * 256u + threadIdx.x) * (uint32_t)ipt;
@@ -182,7 +229,7 @@ k_scan_apply(uint32_t* __restrict__ counts, uint32_t n, int ipt, const uint32_t*
   uint32_t s = 0;
 #pragma unroll
   for (int k = 0; k < kScanMaxIpt; k++) {
-    v[k] = (k < ipt && base + k < n) ? counts[base + k] : 0u;
+    v[k] = (k < ipt && base + k < n) ? ((counts[base + k] + pad) & ~pad) : 0u;
     s += v[k];
   }
   sh[threadIdx.x] = s;
@@ -205,28 +252,30 @@ k_scan_apply(uint32_t* __restrict__ counts, uint32_t n, int ipt, const uint32_t*
   }
 }
 
-// counts[0..n) -> offsets[0..n] (exclusive prefix, total in offsets[n]); counts zeroed; bsum: 4096 words
-cudaError_t launch_exclusive_scan(uint32_t* counts, uint32_t n, uint32_t* bsum, uint32_t* offsets, cudaStream_t st) {
+// counts[0..n) -> offsets[0..n] (exclusive prefix, total in offsets[n]); counts zeroed; bsum: 4096 words.
+// pad = 2^R - 1 rounds every count up to a multiple of 2^R first (batch-affine layout).
+cudaError_t launch_exclusive_scan(uint32_t* counts, uint32_t n, uint32_t* bsum, uint32_t* offsets, cudaStream_t st,
+                                  uint32_t pad) {
   if (n == 0) return cudaMemsetAsync(offsets, 0, 4, st);
   int ipt = 4;
   while ((uint64_t)4096 * 256 * ipt < n && ipt < kScanMaxIpt) ipt *= 2;
   uint32_t per = 256u * (uint32_t)ipt;
   uint32_t nblk = (n + per - 1) / per;
   if (nblk > 4096) return cudaErrorInvalidValue;
-  k_scan_block_sums<<<nblk, 256, 0, st>>>(counts, n, ipt, bsum);
+  k_scan_block_sums<<<nblk, 256, 0, st>>>(counts, n, ipt, pad, bsum);
   k_scan_top<<<1, 1024, 0, st>>>(bsum, nblk);
-  k_scan_apply<<<nblk, 256, 0, st>>>(counts, n, ipt, bsum, offsets);
+  k_scan_apply<<<nblk, 256, 0, st>>>(counts, n, ipt, pad, bsum, offsets);
   return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------- large buckets
 // meta[0] = number of large buckets, meta[1] = number of slices
 __global__ void __launch_bounds__(256)
-k_big_mark_large(const uint32_t* __restrict__ offsets, uint32_t nb, uint32_t large_thresh,
+k_big_mark_large(const uint32_t* __restrict__ offsets, int shift, uint32_t nb, uint32_t large_thresh,
                  uint32_t* __restrict__ meta, BigLargeRec* __restrict__ large, BigSliceRec* __restrict__ slices) {
   uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
-  uint32_t s = offsets[b], cnt = offsets[b + 1] - s;
+  uint32_t s = offsets[b] >> shift, cnt = (offsets[b + 1] >> shift) - s;
   if (cnt <= large_thresh) return;
   uint32_t ns = (cnt + kBigSliceLen - 1) / kBigSliceLen;
   uint32_t li = atomicAdd(&meta[0], 1u);
@@ -255,9 +304,9 @@ __device__ __forceinline__ void big_cta_tree(G1Xyzz* sh, const G1Xyzz& mine) {
   }
 }
 
+template <bool DIRECT>
 __global__ void __launch_bounds__(kBigCtaThreads)
-k_big_slice(const G1Affine* __restrict__ points, const G1Affine* __restrict__ phi, uint32_t n,
-            const uint32_t* __restrict__ entries, const uint32_t* __restrict__ meta,
+k_big_slice(const BigSrc src, const uint32_t* __restrict__ meta,
             const BigSliceRec* __restrict__ slices, G1Xyzz* __restrict__ slice_out) {
   __shared__ G1Xyzz sh[kBigCtaThreads];
   const uint32_t nslices = meta[1];
@@ -268,10 +317,7 @@ k_big_slice(const G1Affine* __restrict__ points, const G1Affine* __restrict__ ph
     xyzz_set_inf(acc);
 #pragma unroll 1
     for (uint32_t t = threadIdx.x; t < r.count; t += kBigCtaThreads) {
-      uint32_t en = entries[r.first + t];
-      uint32_t pi = en & 0x7fffffffu;
-      G1Affine q = pi < n ? points[pi] : phi[pi - n];
-      if (en >> 31) FpM::neg(q.y, q.y);
+      const G1Affine q = big_src_load<DIRECT>(src, r.first + t);
       xyzz_add_mixed(acc, acc, q);
     }
     big_cta_tree(sh, acc);
@@ -305,20 +351,20 @@ k_big_large_finish(const uint32_t* __restrict__ meta, const BigLargeRec* __restr
 // Buckets are handed to threads in order of decreasing length (a counting sort on the
 // length), so the 32 buckets of a warp have (almost) the same trip count and no lane waits
 // for a longer neighbour.  Lengths above kBigLargeBucket count as 0 (slice path).
-__device__ __forceinline__ uint32_t big_size_bin(const uint32_t* __restrict__ offsets, uint32_t b, uint32_t large_thresh) {
-  uint32_t cnt = offsets[b + 1] - offsets[b];
+__device__ __forceinline__ uint32_t big_size_bin(const uint32_t* __restrict__ offsets, int shift, uint32_t b, uint32_t large_thresh) {
+  uint32_t cnt = (offsets[b + 1] >> shift) - (offsets[b] >> shift);
   if (cnt > large_thresh) cnt = 0;
   return large_thresh - cnt;  // bin 0 = longest
 }
 
 template <int PASS>
 __global__ void __launch_bounds__(256)
-k_big_size_sort(const uint32_t* __restrict__ offsets, uint32_t nb, uint32_t large_thresh,
+k_big_size_sort(const uint32_t* __restrict__ offsets, int shift, uint32_t nb, uint32_t large_thresh,
                 uint32_t* __restrict__ bin_counters, const uint32_t* __restrict__ bin_offsets,
                 uint32_t* __restrict__ order) {
   const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t lane = threadIdx.x & 31;
-  uint32_t bin = b < nb ? big_size_bin(offsets, b, large_thresh) : 0xffffffffu;
+  uint32_t bin = b < nb ? big_size_bin(offsets, shift, b, large_thresh) : 0xffffffffu;
   uint32_t peers = __match_any_sync(0xffffffffu, bin);
   uint32_t leader = __ffs(peers) - 1;
   uint32_t rank = __popc(peers & ((1u << lane) - 1u));
@@ -328,25 +374,115 @@ k_big_size_sort(const uint32_t* __restrict__ offsets, uint32_t nb, uint32_t larg
   if (PASS == 1 && bin != 0xffffffffu) order[bin_offsets[bin] + base + rank] = b;
 }
 
+// ---------------------------------------------------------------- batch-affine rounds
+// Round r sums the slots (2k, 2k + 1) of its input (the sorted entries in round 1, the previous
+// round's sums afterwards) into slot k of its output.  Every bucket's region starts at a multiple of
+// 2^R slots and spans a multiple of 2^R, so pairs never straddle two buckets and the regions are
+// offsets >> r after round r; padding slots hold infinity.  total_ptr -> offsets[nb] (the padded
+// number of entries, known only on the device); the grid is sized by its host-side upper bound.
+//
+// A CTA owns kBaThreads * bpt consecutive pairs, thread t the pairs base + t + j * kBaThreads (so a
+// warp's loads and stores are contiguous), and the pairs of a thread share one inversion
+// (batch_affine.cuh): k_ba_fwd leaves the running products of the denominators in pre[] and the
+// thread's total in totals[]; k_ba_inv inverts all totals (the same trick one level up, one real
+// inversion per thread); k_ba_bwd peels the factors off and writes the sums.
+constexpr int kBaThreads = 128;
+
+template <bool DIRECT>
+__global__ void __launch_bounds__(kBaThreads)
+k_ba_fwd(const BigSrc src, const uint32_t* __restrict__ total_ptr, int shift, int bpt, Fp* __restrict__ pre,
+         Fp* __restrict__ totals) {
+  const uint32_t npairs = (total_ptr[0] >> shift) >> 1;
+  uint32_t k = blockIdx.x * (uint32_t)(kBaThreads * bpt) + threadIdx.x;
+  Fp run;
+  FpM::set_one(run);
+#pragma unroll 1
+  for (int j = 0; j < bpt && k < npairs; j++, k += kBaThreads) {
+    const Fp x1 = big_src_load_x<DIRECT>(src, 2 * k), x2 = big_src_load_x<DIRECT>(src, 2 * k + 1);
+    Fp d;
+    FpM::sub(d, x2, x1);
+    if (FpM::is_zero(d)) {  // rare: equal points, opposite points, padding
+      const G1Affine p1 = big_src_load<DIRECT>(src, 2 * k), p2 = big_src_load<DIRECT>(src, 2 * k + 1);
+      ba_denominator_equal_x(d, p1.y, p2.y);
+    }
+    if (j == 0) run = d;
+    else FpM::mul(run, run, d);
+    pre[k] = run;
+  }
+  totals[blockIdx.x * kBaThreads + threadIdx.x] = run;
+}
+
+// totals[i] <- 1 / totals[i]; thread t of a CTA owns the G totals base + t + j * blockDim
+__global__ void __launch_bounds__(kBaThreads)
+k_ba_inv(Fp* __restrict__ totals, Fp* __restrict__ tpre, uint32_t ntot, int G) {
+  const uint32_t first = blockIdx.x * (uint32_t)(kBaThreads * G) + threadIdx.x;
+  if (first >= ntot) return;
+  Fp run = totals[first];
+  int cnt = 1;
+#pragma unroll 1
+  for (uint32_t i = first + kBaThreads; cnt < G && i < ntot; i += kBaThreads, cnt++) {
+    tpre[i - kBaThreads] = run;
+    const Fp t = totals[i];
+    FpM::mul(run, run, t);
+  }
+  Fp inv;
+  fp_inv(inv, run);
+#pragma unroll 1
+  for (int j = cnt - 1; j >= 1; j--) {
+    const uint32_t i = first + (uint32_t)j * kBaThreads;
+    const Fp t = totals[i], p = tpre[i - kBaThreads];
+    Fp o;
+    FpM::mul(o, inv, p);
+    totals[i] = o;
+    FpM::mul(inv, inv, t);
+  }
+  totals[first] = inv;
+}
+
+template <bool DIRECT>
+__global__ void __launch_bounds__(kBaThreads)
+k_ba_bwd(const BigSrc src, const uint32_t* __restrict__ total_ptr, int shift, int bpt, const Fp* __restrict__ pre,
+         const Fp* __restrict__ totals, G1Affine* __restrict__ dst) {
+  const uint32_t npairs = (total_ptr[0] >> shift) >> 1;
+  const uint32_t k0 = blockIdx.x * (uint32_t)(kBaThreads * bpt) + threadIdx.x;
+  if (k0 >= npairs) return;
+  uint32_t cnt = (npairs - k0 + kBaThreads - 1) / kBaThreads;
+  if (cnt > (uint32_t)bpt) cnt = (uint32_t)bpt;
+  Fp inv = totals[blockIdx.x * kBaThreads + threadIdx.x];
+#pragma unroll 1
+  for (int j = (int)cnt - 1; j >= 0; j--) {
+    const uint32_t k = k0 + (uint32_t)j * kBaThreads;
+    const G1Affine p1 = big_src_load<DIRECT>(src, 2 * k), p2 = big_src_load<DIRECT>(src, 2 * k + 1);
+    Fp invj = inv;
+    if (j > 0) {
+      Fp d;
+      ba_denominator(d, p1, p2);
+      const Fp pj = pre[k - kBaThreads];
+      FpM::mul(invj, inv, pj);
+      FpM::mul(inv, inv, d);
+    }
+    G1Affine r;
+    ba_pair_sum(r, p1, p2, invj);
+    dst[k] = r;
+  }
+}
+
 // ---------------------------------------------------------------- bucket accumulation
+template <bool DIRECT>
 __global__ void __launch_bounds__(128, 3)
-k_big_accum(const G1Affine* __restrict__ points, const G1Affine* __restrict__ phi, uint32_t n,
-            const uint32_t* __restrict__ entries, const uint32_t* __restrict__ offsets,
+k_big_accum(const BigSrc src, const uint32_t* __restrict__ offsets, int shift,
             const uint32_t* __restrict__ order, uint32_t nb, uint32_t large_thresh,
             G1Xyzz* __restrict__ buckets) {
   uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= nb) return;
   const uint32_t b = order[tid];
-  uint32_t s = offsets[b], e = offsets[b + 1];
+  uint32_t s = offsets[b] >> shift, e = offsets[b + 1] >> shift;
   G1Xyzz acc;
   xyzz_set_inf(acc);
   if (e - s <= large_thresh) {
 #pragma unroll 1
     for (uint32_t t = s; t < e; t++) {
-      uint32_t en = entries[t];
-      uint32_t pi = en & 0x7fffffffu;
-      G1Affine q = pi < n ? points[pi] : phi[pi - n];
-      if (en >> 31) FpM::neg(q.y, q.y);
+      const G1Affine q = big_src_load<DIRECT>(src, t);
       xyzz_add_mixed(acc, acc, q);
     }
   }
@@ -522,7 +658,22 @@ int big_msm_pick_c(size_t n) {
   return lg <= 20 ? table[lg] : 16;
 }
 
-BigMsmDims big_msm_dims(size_t n, int c, int wfirst, int wstep) {
+// Batch-affine rounds by the mean number of entries per bucket: a round halves every bucket at 6.3
+// instead of 10 products per addition, but pads every bucket to a multiple of 2^R slots (2^R / 2 wasted
+// pair slots on average) and costs three more launches; below ~ 32 entries per bucket it does not pay.
+static int big_msm_pick_rounds(size_t mean) {
+  static const int forced = [] {
+    const char* e = getenv("CDL_MSM_BATCH_AFFINE");
+    return e ? atoi(e) : -1;
+  }();
+  if (forced >= 0) return forced > kBigMaxBaRounds ? kBigMaxBaRounds : forced;
+  int lg = 0;
+  while (((size_t)2 << lg) <= mean) lg++;
+  int r = lg - 4;  // leaves 16 .. 31 points per bucket to the XYZZ pass
+  return r < 0 ? 0 : r > kBigMaxBaRounds ? kBigMaxBaRounds : r;
+}
+
+BigMsmDims big_msm_dims(size_t n, int c, int wfirst, int wstep, int ba_rounds) {
   BigMsmDims d;
   d.n = (int)n;
   d.c = c;
@@ -532,32 +683,45 @@ BigMsmDims big_msm_dims(size_t n, int c, int wfirst, int wstep) {
   d.wstep = wstep;
   d.nlocal = wfirst < d.W ? (d.W - wfirst + wstep - 1) / wstep : 0;
   d.nb = (uint32_t)d.nlocal * (uint32_t)d.M;
-  // a bucket longer than 8x the mean goes to the CTA-per-slice path instead of one thread
-  // (degenerate scalars, and the top window, which holds only 256 - c*(W-1) scalar bits)
   size_t mean = 2 * n / (size_t)d.M + 1;
-  size_t lt = 8 * mean;
+  d.R = ba_rounds >= 0 ? (ba_rounds > kBigMaxBaRounds ? kBigMaxBaRounds : ba_rounds) : big_msm_pick_rounds(mean);
+  if (d.nlocal == 0 || n == 0) d.R = 0;
+  // a bucket longer than 8x the mean goes to the CTA-per-slice path instead of one thread
+  // (degenerate scalars, and the top window, which holds only 256 - c*(W-1) scalar bits);
+  // lengths are those the XYZZ pass sees, i.e. after the batch-affine rounds
+  size_t lt = 8 * ((mean >> d.R) + 1);
   d.large = (uint32_t)(lt < 64 ? 64 : lt > kBigLargeBucket ? kBigLargeBucket : lt);
   return d;
 }
 
 static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+// pairs per thread of a batch-affine round: 16 when the round fills the machine several times over,
+// fewer (never under 2) for the small late rounds, whose threads would otherwise be too few
+static int ba_pairs_per_thread(uint64_t npairs, int sm_count) {
+  uint64_t want_threads = (uint64_t)sm_count * 1024;
+  uint64_t b = npairs / want_threads;
+  return b < 2 ? 2 : b > 16 ? 16 : (int)b;
+}
+
 struct BigLayout {
-  size_t counts, offsets, bsum, meta, entries, buckets, large, slices, slice_out, red0, red1, bins, bin_off, order, phi, total;
+  size_t counts, offsets, bsum, meta, entries, buckets, large, slices, slice_out, red0, red1, bins, bin_off, order, phi;
+  size_t work0, work1, pre, totals, tpre, total;
   uint32_t max_slices, max_large;
 };
 
 static BigLayout big_layout(const BigMsmDims& d) {
   BigLayout L;
-  size_t nent = 2 * (size_t)d.n * (size_t)d.nlocal;
-  L.max_large = (uint32_t)(nent / d.large + 1);
-  L.max_slices = (uint32_t)(nent / kBigSliceLen + L.max_large + 1);
+  size_t nent = (size_t)big_msm_entries(d);  // padded upper bound
+  size_t nfinal = nent >> d.R;               // summands left for the XYZZ pass
+  L.max_large = (uint32_t)(nfinal / d.large + 1);
+  L.max_slices = (uint32_t)(nfinal / kBigSliceLen + L.max_large + 1);
   size_t o = 0;
   L.counts = o; o += al256(((size_t)d.nb + 1) * 4);
   L.offsets = o; o += al256(((size_t)d.nb + 2) * 4);
   L.bsum = o; o += al256(4096 * 4);
   L.meta = o; o += 256;
-  L.entries = o; o += al256((nent + 1) * 4);
+  L.entries = o; o += al256((nent + 2) * 4);
   L.buckets = o; o += al256(((size_t)d.nb + 1) * sizeof(G1Xyzz));
   L.large = o; o += al256((size_t)L.max_large * sizeof(BigLargeRec));
   L.slices = o; o += al256((size_t)L.max_slices * sizeof(BigSliceRec));
@@ -569,6 +733,17 @@ static BigLayout big_layout(const BigMsmDims& d) {
   L.bin_off = o; o += al256(((size_t)kBigLargeBucket + 3) * 4);
   L.order = o; o += al256(((size_t)d.nb + 1) * 4);
   L.phi = o; o += al256(((size_t)d.n + 1) * sizeof(G1Affine));
+  L.work0 = L.work1 = L.pre = L.totals = L.tpre = o;
+  if (d.R > 0) {
+    size_t p1 = nent / 2 + 1;  // pairs of round 1
+    // a thread owns at least 2 pairs; every CTA writes kBaThreads totals
+    size_t ntot = (p1 / 2 / kBaThreads + 2) * kBaThreads;
+    L.work0 = o; o += al256(p1 * sizeof(G1Affine));
+    L.work1 = o; o += al256((p1 / 2 + 1) * sizeof(G1Affine));
+    L.pre = o; o += al256(p1 * sizeof(Fp));
+    L.totals = o; o += al256(ntot * sizeof(Fp));
+    L.tpre = o; o += al256(ntot * sizeof(Fp));
+  }
   L.total = o;
   return L;
 }
@@ -605,23 +780,56 @@ cudaError_t launch_big_msm(const G1Affine* points, const Fr* scalars, const BigM
     return cudaGetLastError();
   }
   const uint32_t nb = d.nb;
+  const int R = d.R;
+  const uint64_t nent = big_msm_entries(d);
   cudaMemsetAsync(counts, 0, ((size_t)nb + 1) * 4, st);
   cudaMemsetAsync(meta, 0, 256, st);
   const int gd = (d.n + 255) / 256;
   k_big_phi<<<gd, 256, 0, st>>>(points, d.n, phi);
   k_big_digits<0><<<gd, 256, 0, st>>>(scalars, d.n, d, counts, nullptr, nullptr);
-  cudaError_t se = launch_exclusive_scan(counts, nb, bsum, offsets, st);
+  cudaError_t se = launch_exclusive_scan(counts, nb, bsum, offsets, st, (1u << R) - 1u);
   if (se != cudaSuccess) return se;
+  if (R > 0) cudaMemsetAsync(entries, 0xff, (size_t)(nent + 2) * 4, st);  // padding slots = infinity
   k_big_digits<1><<<gd, 256, 0, st>>>(scalars, d.n, d, counts, offsets, entries);
-  k_big_mark_large<<<(nb + 255) / 256, 256, 0, st>>>(offsets, nb, d.large, meta, large, slices);
+
+  BigSrc src{points, phi, (uint32_t)d.n, entries, nullptr};
+  if (R > 0) {
+    G1Affine* work[2] = {(G1Affine*)(base + L.work0), (G1Affine*)(base + L.work1)};
+    Fp* pre = (Fp*)(base + L.pre);
+    Fp* totals = (Fp*)(base + L.totals);
+    Fp* tpre = (Fp*)(base + L.tpre);
+    for (int r = 1; r <= R; r++) {
+      const uint64_t npairs = nent >> r;  // upper bound; the kernels read the exact count
+      if (npairs == 0) break;
+      const int bpt = ba_pairs_per_thread(npairs, sm_count);
+      const uint32_t nblk = (uint32_t)((npairs + (uint64_t)kBaThreads * bpt - 1) / ((uint64_t)kBaThreads * bpt));
+      const uint32_t ntot = nblk * (uint32_t)kBaThreads;
+      int G = (int)(ntot / ((uint32_t)sm_count * 512u));
+      G = G < 1 ? 1 : G > 32 ? 32 : G;
+      G1Affine* dst = work[(r - 1) & 1];
+      if (r == 1) k_ba_fwd<false><<<nblk, kBaThreads, 0, st>>>(src, offsets + nb, r - 1, bpt, pre, totals);
+      else k_ba_fwd<true><<<nblk, kBaThreads, 0, st>>>(src, offsets + nb, r - 1, bpt, pre, totals);
+      k_ba_inv<<<(ntot + kBaThreads * G - 1) / (kBaThreads * G), kBaThreads, 0, st>>>(totals, tpre, ntot, G);
+      if (r == 1) k_ba_bwd<false><<<nblk, kBaThreads, 0, st>>>(src, offsets + nb, r - 1, bpt, pre, totals, dst);
+      else k_ba_bwd<true><<<nblk, kBaThreads, 0, st>>>(src, offsets + nb, r - 1, bpt, pre, totals, dst);
+      src.direct = dst;
+    }
+  }
+
+  k_big_mark_large<<<(nb + 255) / 256, 256, 0, st>>>(offsets, R, nb, d.large, meta, large, slices);
   const uint32_t nbins = d.large + 1;
   cudaMemsetAsync(bins, 0, ((size_t)nbins + 1) * 4, st);
-  k_big_size_sort<0><<<(nb + 255) / 256, 256, 0, st>>>(offsets, nb, d.large, bins, nullptr, nullptr);
+  k_big_size_sort<0><<<(nb + 255) / 256, 256, 0, st>>>(offsets, R, nb, d.large, bins, nullptr, nullptr);
   se = launch_exclusive_scan(bins, nbins, bsum, bin_off, st);
   if (se != cudaSuccess) return se;
-  k_big_size_sort<1><<<(nb + 255) / 256, 256, 0, st>>>(offsets, nb, d.large, bins, bin_off, order);
-  k_big_accum<<<(nb + 127) / 128, 128, 0, st>>>(points, phi, (uint32_t)d.n, entries, offsets, order, nb, d.large, buckets);
-  k_big_slice<<<sm_count * 4, kBigCtaThreads, 0, st>>>(points, phi, (uint32_t)d.n, entries, meta, slices, slice_out);
+  k_big_size_sort<1><<<(nb + 255) / 256, 256, 0, st>>>(offsets, R, nb, d.large, bins, bin_off, order);
+  if (src.direct) {
+    k_big_accum<true><<<(nb + 127) / 128, 128, 0, st>>>(src, offsets, R, order, nb, d.large, buckets);
+    k_big_slice<true><<<sm_count * 4, kBigCtaThreads, 0, st>>>(src, meta, slices, slice_out);
+  } else {
+    k_big_accum<false><<<(nb + 127) / 128, 128, 0, st>>>(src, offsets, R, order, nb, d.large, buckets);
+    k_big_slice<false><<<sm_count * 4, kBigCtaThreads, 0, st>>>(src, meta, slices, slice_out);
+  }
   k_big_large_finish<<<sm_count, kBigCtaThreads, 0, st>>>(meta, large, slice_out, buckets);
   // bucket reduction
   int Lc = d.M < 8 ? d.M : 8;  // buckets per reduce1 thread: shorter serial chain, more threads

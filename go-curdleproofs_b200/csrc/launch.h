@@ -86,7 +86,8 @@ inline void msm_build_subs(const MsmTask* tasks, size_t ntasks, uint32_t chunk, 
 }
 
 // counts[0..n) -> offsets[0..n] exclusive prefix (total in offsets[n]); counts are zeroed; bsum: 4096 words
-cudaError_t launch_exclusive_scan(uint32_t* counts, uint32_t n, uint32_t* bsum, uint32_t* offsets, cudaStream_t st);
+cudaError_t launch_exclusive_scan(uint32_t* counts, uint32_t n, uint32_t* bsum, uint32_t* offsets, cudaStream_t st,
+                                  uint32_t pad = 0);
 
 // Latency path (k_msm.cu): one CTA per task.  Callers switch to the throughput path at
 // kMsmSplitThreshold tasks per launch.
@@ -103,14 +104,20 @@ void launch_msm_small(const G1Affine* points, const uint32_t* idx, const Fr* sca
 struct BigMsmDims {
   int n, c, W, M, wfirst, wstep, nlocal;
   uint32_t nb;     // nlocal * M buckets
-  uint32_t large;  // buckets with more entries than this are summed by whole CTAs (slices)
+  uint32_t large;  // buckets with more entries than this (after the batch-affine rounds) are summed by whole CTAs (slices)
+  int R;           // batch-affine rounds: bucket regions padded to 2^R slots and halved R times (0 = XYZZ only)
 };
 constexpr size_t kBigMsmThreshold = 1024;  // cdl_g1_msm switches to the Pippenger path above this size
 int big_msm_pick_c(size_t n);
-BigMsmDims big_msm_dims(size_t n, int c, int wfirst, int wstep);
+// ba_rounds < 0: pick the number of batch-affine rounds by the mean bucket load
+BigMsmDims big_msm_dims(size_t n, int c, int wfirst, int wstep, int ba_rounds = -1);
+constexpr int kBigMaxBaRounds = 8;
 size_t big_msm_scratch_bytes(const BigMsmDims& d);
-// sorted (point, sign) entries of a launch: both GLV halves of every term in every owned window
-inline uint64_t big_msm_entries(const BigMsmDims& d) { return 2ull * (uint64_t)d.n * (uint64_t)d.nlocal; }
+// sorted (point, sign) entries of a launch: both GLV halves of every term in every owned window, plus
+// the padding of every bucket's region to a multiple of 2^R slots (upper bound)
+inline uint64_t big_msm_entries(const BigMsmDims& d) {
+  return 2ull * (uint64_t)d.n * (uint64_t)d.nlocal + (uint64_t)d.nb * (((uint64_t)1 << d.R) - 1);
+}
 cudaError_t launch_big_msm(const G1Affine* points, const Fr* scalars, const BigMsmDims& d, int normalize,
                            void* scratch, int sm_count, G1Jac* d_out, cudaStream_t st);
 void launch_big_combine(const G1Jac* in, int n, G1Jac* out, cudaStream_t st);

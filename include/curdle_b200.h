@@ -272,6 +272,12 @@ int32_t cdl_g1_msm_device(cdl_ctx* ctx, const cdl_g1_affine* d_points, const cdl
 /* Override the Pippenger window width (2..18 bits; 0 = choose by size).  Tuning aid;
  * the result does not depend on it.  Also settable as environment CDL_MSM_C. */
 int32_t cdl_set_msm_window(cdl_ctx* ctx, int32_t window_bits);
+/* Number of batch-affine rounds of the large MSM's bucket accumulation (0..8; -1 = choose by the
+ * mean bucket load; 0 = extended-Jacobian buckets only): for `rounds` rounds neighbouring summands
+ * of every bucket are added as affine points whose inversions are shared by Montgomery's trick
+ * (what gnark-crypto's MultiExp does for its large windows).  Tuning aid; the result does not
+ * depend on it.  Also settable as environment CDL_MSM_BATCH_AFFINE. */
+int32_t cdl_set_msm_batch_affine(cdl_ctx* ctx, int32_t rounds);
 
 /* One process per GPU: rank 0 calls cdl_comm_unique_id, the host application
  * ships the 128 bytes to every rank (any transport), every rank calls

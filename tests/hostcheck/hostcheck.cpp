@@ -4,6 +4,7 @@
 // not part of the shipped library and is never used as a fallback.
 #include <cstring>
 #include "../../go-curdleproofs_b200/csrc/g1.cuh"
+#include "../../go-curdleproofs_b200/csrc/batch_affine.cuh"
 
 using namespace cdl;
 
@@ -83,5 +84,31 @@ void hc_g1_in_subgroup(const G1Affine* p, int* out, int n) {
 }
 
 int hc_on_curve(const G1Affine* p) { return aff_on_curve(*p); }
+
+// r[i] = a[i] + b[i] as ONE batch-affine run (forward products, one inversion, backward peel): the
+// per-thread schedule of k_ba_fwd / k_ba_bwd (csrc/k_msm_big.cu) on the host
+void hc_batch_affine(const G1Affine* a, const G1Affine* b, G1Affine* r, Fp* pre, int n) {
+  Fp run;
+  FpM::set_one(run);
+  for (int j = 0; j < n; j++) {
+    Fp d;
+    ba_denominator(d, a[j], b[j]);
+    if (j == 0) run = d;
+    else FpM::mul(run, run, d);
+    pre[j] = run;
+  }
+  Fp inv;
+  fp_inv(inv, run);
+  for (int j = n - 1; j >= 0; j--) {
+    Fp invj = inv;
+    if (j > 0) {
+      Fp d;
+      ba_denominator(d, a[j], b[j]);
+      FpM::mul(invj, inv, pre[j - 1]);
+      FpM::mul(inv, inv, d);
+    }
+    ba_pair_sum(r[j], a[j], b[j], invj);
+  }
+}
 
 }  // extern "C"

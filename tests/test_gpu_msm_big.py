@@ -63,7 +63,38 @@ def test_big_msm_every_window_width(ctx, sweep, c):
     assert got == expected(a[:n], s[:n])
 
 
-def test_big_msm_adversarial(ctx, sweep):
+@pytest.mark.parametrize("c,rounds", [(8, 1), (8, 2), (8, 3), (8, 5), (8, 8), (11, 4), (5, 6), (13, 1), (16, 2)])
+def test_big_msm_batch_affine_rounds(ctx, sweep, c, rounds):
+    """Batch-affine bucket accumulation (cdl_set_msm_batch_affine): any number of pair-sum rounds, more
+    than the buckets hold included, gives the same point as the extended-Jacobian buckets alone."""
+    a, s, pts = sweep
+    n = 1 << 14
+    ctx.set_msm_window(c)
+    try:
+        ctx.set_msm_batch_affine(0)
+        plain = ctx.g1_msm(pts[: 96 * n], frs_enc(s[:n]))
+        ctx.set_msm_batch_affine(rounds)
+        got = ctx.g1_msm(pts[: 96 * n], frs_enc(s[:n]))
+        odd = jac_dec(ctx.g1_msm(pts[: 96 * 4099], frs_enc(s[:4099])))
+    finally:
+        ctx.set_msm_window(0)
+        ctx.set_msm_batch_affine(-1)
+    assert got == plain and jac_dec(got) == expected(a[:n], s[:n])
+    assert odd == expected(a[:4099], s[:4099])
+
+
+@pytest.mark.parametrize("c,rounds", [(0, -1), (9, 3), (12, 2), (7, 7)])
+def test_big_msm_adversarial(ctx, sweep, c, rounds):
+    ctx.set_msm_window(c)
+    ctx.set_msm_batch_affine(rounds)
+    try:
+        _adversarial(ctx, sweep)
+    finally:
+        ctx.set_msm_window(0)
+        ctx.set_msm_batch_affine(-1)
+
+
+def _adversarial(ctx, sweep):
     a, s, pts = sweep
     n = 1 << 14
     random.seed(9)
@@ -167,6 +198,12 @@ def test_big_msm_2_20_property(ctx, sweep):
     sc = []
     for m in mults:
         sc.extend(x * m % R for x in s)
-    got = jac_dec(ctx.g1_msm(pts * reps, frs_enc(sc)))
     tot = sum(x * y for x, y in zip(a, s)) % R
-    assert got == b.g1_mul(b.G1_GEN, tot * sum(mults) % R)
+    want = b.g1_mul(b.G1_GEN, tot * sum(mults) % R)
+    for rounds in (-1, 0, 3):  # chosen by bucket load / extended-Jacobian buckets only / three batch-affine rounds
+        ctx.set_msm_batch_affine(rounds)
+        try:
+            got = jac_dec(ctx.g1_msm(pts * reps, frs_enc(sc)))
+        finally:
+            ctx.set_msm_batch_affine(-1)
+        assert got == want

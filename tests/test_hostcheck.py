@@ -193,3 +193,20 @@ def test_endomorphism_subgroup_check(hc):
     hc.hc_g1_in_subgroup(b"".join(aff_enc(p) for p in pts), out, len(pts))
     assert list(out) == [1] * len(good) + [0] * len(bad)
     assert [int(b.g1_in_subgroup(p)) for p in pts] == list(out)
+
+
+def test_batch_affine_run_all_cases(hc):
+    """One batch-affine run (csrc/batch_affine.cuh: shared inversion by Montgomery's trick) over pairs that
+    include every exceptional case — doubling, P - P, infinity on either or both sides — in the middle of
+    ordinary pairs, against the oracle's affine addition."""
+    random.seed(17)
+    pts = [b.g1_mul(b.G1_GEN, random.randrange(R)) for _ in range(40)]
+    As = pts[:10] + [None, pts[0], pts[1], None, pts[2]] + pts[10:20] + [pts[5], None]
+    Bs = pts[20:30] + [pts[3], None, b.g1_neg(pts[1]), None, pts[2]] + pts[30:40] + [b.g1_neg(pts[5]), None]
+    for lo, hi in ((0, len(As)), (10, 15), (12, 13), (14, 15), (3, 4)):
+        A, Bv = As[lo:hi], Bs[lo:hi]
+        out = ctypes.create_string_buffer(96 * len(A))
+        pre = ctypes.create_string_buffer(48 * len(A))
+        hc.hc_batch_affine(b"".join(aff_enc(p) for p in A), b"".join(aff_enc(p) for p in Bv), out, pre, len(A))
+        got = [aff_dec(out.raw[i * 96:(i + 1) * 96]) for i in range(len(A))]
+        assert got == [b.g1_add(x, y) for x, y in zip(A, Bv)]
