@@ -4,7 +4,8 @@
 // gnark's MultiExp is reached from msmaccumulator/msmaccumulator.go:59 and
 // common/util.go:75 with the same signature).
 //
-//   k_big_phi        phi(P) = (beta*x, y) for every base (GLV endomorphism)
+//   k_big_tables     gather table of the bases: P and phi(P) = (beta*x, y) (the GLV endomorphism),
+//                    one 128-byte line each
 //   k_big_digits<0>  thread per scalar: Montgomery -> canonical -> GLV halves (< 2^127),
 //                    signed c-bit digits d_w in [-2^(c-1), 2^(c-1)] of both halves,
 //                    histogram of (window, |d|) keys
@@ -53,12 +54,21 @@ struct BigLargeRec {
   uint32_t bucket, slice_first, slice_count, pad;
 };
 
-// Where the summands of a bucket come from: the sorted entries (a gather from [points | phi],
-// bit 31 = negate, an index beyond both tables = padding = infinity), or — after batch-affine
+// The bucket sums gather their operands at random, and a random read costs a whole 128-byte L2 line
+// of DRAM traffic whatever its size (measured: 117 B per 48-byte coordinate in a 64-byte slot, 257 B per
+// point as two such slots, 203 B per 96-byte point straddling lines).  So the bases are re-laid once
+// per MSM as one table of 2n points, tab[0 .. n) = P and tab[n .. 2n) = phi(P) = (beta * x, y) (the GLV
+// endomorphism), each in its own 128-byte line: a gathered point, or its x alone, is exactly one line.
+struct alignas(128) BigPoint {
+  Fp x, y;
+  uint32_t pad[8];
+};
+
+// Where the summands of a bucket come from: the sorted entries (a gather from the coordinate tables,
+// bit 31 = negate, an index beyond the tables = padding = infinity), or — after batch-affine
 // rounds — the affine pair sums of the last round, in place.
 struct BigSrc {
-  const G1Affine* points;
-  const G1Affine* phi;
+  const BigPoint* tab;  // 2n slots: [P | phi(P)]
   uint32_t n;
   const uint32_t* entries;
   const G1Affine* direct;  // non-null: slot t holds its point
@@ -73,7 +83,8 @@ __device__ __forceinline__ G1Affine big_src_load(const BigSrc& s, uint32_t t) {
     aff_set_inf(q);
     return q;
   }
-  q = pi < s.n ? s.points[pi] : s.phi[pi - s.n];
+  q.x = s.tab[pi].x;
+  q.y = s.tab[pi].y;
   if (en >> 31) FpM::neg(q.y, q.y);
   return q;
 }
@@ -81,13 +92,13 @@ __device__ __forceinline__ G1Affine big_src_load(const BigSrc& s, uint32_t t) {
 template <bool DIRECT>
 __device__ __forceinline__ Fp big_src_load_x(const BigSrc& s, uint32_t t) {
   if (DIRECT) return s.direct[t].x;
-  Fp x;
   const uint32_t pi = s.entries[t] & 0x7fffffffu;
   if (pi >= 2u * s.n) {
+    Fp x;
     FpM::set_zero(x);
     return x;
   }
-  return pi < s.n ? s.points[pi].x : s.phi[pi - s.n].x;
+  return s.tab[pi].x;
 }
 
 // ---------------------------------------------------------------- digits
@@ -106,17 +117,20 @@ __device__ __forceinline__ uint32_t big_raw_digit(const uint32_t* k6, int w, int
 }
 
 __global__ void __launch_bounds__(256)
-k_big_phi(const G1Affine* __restrict__ points, int n, G1Affine* __restrict__ phi) {
+k_big_tables(const G1Affine* __restrict__ points, int n, BigPoint* __restrict__ tab) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  G1Affine p = points[i];
-  Fp beta;
+  const G1Affine p = points[i];
+  Fp beta, bx;
   fp_set_beta(beta);
-  FpM::mul(p.x, p.x, beta);  // infinity (0, 0) stays (0, 0)
-  phi[i] = p;
+  FpM::mul(bx, p.x, beta);  // infinity (0, 0) stays (0, 0)
+  tab[i].x = p.x;
+  tab[i].y = p.y;
+  tab[i + n].x = bx;
+  tab[i + n].y = p.y;
 }
 
-// entry = index into [points | phi] (bit 31: negate)
+// entry = index into tab[] = [P | phi(P)] (bit 31: negate)
 template <int PASS>
 __global__ void __launch_bounds__(256)
 k_big_digits(const Fr* __restrict__ scalars, int n, BigMsmDims dm, uint32_t* __restrict__ counters,
@@ -381,18 +395,25 @@ k_big_size_sort(const uint32_t* __restrict__ offsets, int shift, uint32_t nb, ui
 // offsets >> r after round r; padding slots hold infinity.  total_ptr -> offsets[nb] (the padded
 // number of entries, known only on the device); the grid is sized by its host-side upper bound.
 //
-// A CTA owns kBaThreads * bpt consecutive pairs, thread t the pairs base + t + j * kBaThreads (so a
-// warp's loads and stores are contiguous), and the pairs of a thread share one inversion
+// The grid is a whole number of waves of resident CTAs and every CTA owns the same number of
+// consecutive pairs, kBaThreads * bpt with bpt = ceil(pairs / threads) — no half-empty last wave.
+// Thread t of a CTA takes the pairs base + t + j * kBaThreads (so a warp's loads and stores are
+// contiguous), and the pairs of a thread share one inversion
 // (batch_affine.cuh): k_ba_fwd leaves the running products of the denominators in pre[] and the
 // thread's total in totals[]; k_ba_inv inverts all totals (the same trick one level up, one real
 // inversion per thread); k_ba_bwd peels the factors off and writes the sums.
 constexpr int kBaThreads = 128;
+__host__ __device__ __forceinline__ uint32_t ba_pairs_per_thread(uint32_t npairs, uint32_t nblk) {
+  const uint32_t threads = nblk * (uint32_t)kBaThreads;
+  return (npairs + threads - 1) / threads;
+}
 
 template <bool DIRECT>
 __global__ void __launch_bounds__(kBaThreads)
-k_ba_fwd(const BigSrc src, const uint32_t* __restrict__ total_ptr, int shift, int bpt, Fp* __restrict__ pre,
+k_ba_fwd(const BigSrc src, const uint32_t* __restrict__ total_ptr, int shift, Fp* __restrict__ pre,
          Fp* __restrict__ totals) {
   const uint32_t npairs = (total_ptr[0] >> shift) >> 1;
+  const int bpt = (int)ba_pairs_per_thread(npairs, gridDim.x);
   uint32_t k = blockIdx.x * (uint32_t)(kBaThreads * bpt) + threadIdx.x;
   Fp run;
   FpM::set_one(run);
@@ -441,9 +462,10 @@ k_ba_inv(Fp* __restrict__ totals, Fp* __restrict__ tpre, uint32_t ntot, int G) {
 
 template <bool DIRECT>
 __global__ void __launch_bounds__(kBaThreads)
-k_ba_bwd(const BigSrc src, const uint32_t* __restrict__ total_ptr, int shift, int bpt, const Fp* __restrict__ pre,
+k_ba_bwd(const BigSrc src, const uint32_t* __restrict__ total_ptr, int shift, const Fp* __restrict__ pre,
          const Fp* __restrict__ totals, G1Affine* __restrict__ dst) {
   const uint32_t npairs = (total_ptr[0] >> shift) >> 1;
+  const int bpt = (int)ba_pairs_per_thread(npairs, gridDim.x);
   const uint32_t k0 = blockIdx.x * (uint32_t)(kBaThreads * bpt) + threadIdx.x;
   if (k0 >= npairs) return;
   uint32_t cnt = (npairs - k0 + kBaThreads - 1) / kBaThreads;
@@ -696,16 +718,35 @@ BigMsmDims big_msm_dims(size_t n, int c, int wfirst, int wstep, int ba_rounds) {
 
 static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-// pairs per thread of a batch-affine round: 16 when the round fills the machine several times over,
-// fewer (never under 2) for the small late rounds, whose threads would otherwise be too few
-static int ba_pairs_per_thread(uint64_t npairs, int sm_count) {
-  uint64_t want_threads = (uint64_t)sm_count * 1024;
-  uint64_t b = npairs / want_threads;
-  return b < 2 ? 2 : b > 16 ? 16 : (int)b;
+// CTAs of a batch-affine round.  The forward and the backward kernel must cut the pairs into the same
+// per-thread runs, so they share the grid: a multiple of the number of CTAs that are resident at once
+// for EITHER kernel (they differ in registers), as many waves as bring a thread's run down to about
+// kBaTargetPairs pairs; a round too small for one such wave gets two pairs per thread.
+constexpr uint32_t kBaTargetPairs = 24;
+static uint32_t ba_grid(uint64_t npairs, int sm_count) {
+  static const uint32_t per_sm = [] {
+    int of = 0, ob = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&of, k_ba_fwd<false>, kBaThreads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ob, k_ba_bwd<false>, kBaThreads, 0);
+    if (of < 1) of = 1;
+    if (ob < 1) ob = 1;
+    uint32_t a = (uint32_t)of, b = (uint32_t)ob, g = a, h = b;
+    while (h) { uint32_t t = g % h; g = h; h = t; }
+    return a / g * b;  // lcm
+  }();
+  static const uint32_t target = [] {
+    const char* e = getenv("CDL_BA_BPT");
+    return e ? (uint32_t)atoi(e) : kBaTargetPairs;
+  }();
+  const uint64_t wave = (uint64_t)per_sm * (uint64_t)sm_count;
+  if (npairs < wave * kBaThreads * 2) return (uint32_t)((npairs + 2 * kBaThreads - 1) / (2 * kBaThreads));
+  uint64_t m = (npairs + wave * kBaThreads * target / 2) / (wave * kBaThreads * target);
+  if (m < 1) m = 1;
+  return (uint32_t)(m * wave);
 }
 
 struct BigLayout {
-  size_t counts, offsets, bsum, meta, entries, buckets, large, slices, slice_out, red0, red1, bins, bin_off, order, phi;
+  size_t counts, offsets, bsum, meta, entries, buckets, large, slices, slice_out, red0, red1, bins, bin_off, order, tab;
   size_t work0, work1, pre, totals, tpre, total;
   uint32_t max_slices, max_large;
 };
@@ -732,7 +773,7 @@ static BigLayout big_layout(const BigMsmDims& d) {
   L.bins = o; o += al256(((size_t)kBigLargeBucket + 2) * 4);
   L.bin_off = o; o += al256(((size_t)kBigLargeBucket + 3) * 4);
   L.order = o; o += al256(((size_t)d.nb + 1) * 4);
-  L.phi = o; o += al256(((size_t)d.n + 1) * sizeof(G1Affine));
+  L.tab = o; o += al256((2 * (size_t)d.n + 1) * sizeof(BigPoint));
   L.work0 = L.work1 = L.pre = L.totals = L.tpre = o;
   if (d.R > 0) {
     size_t p1 = nent / 2 + 1;  // pairs of round 1
@@ -769,7 +810,7 @@ cudaError_t launch_big_msm(const G1Affine* points, const Fr* scalars, const BigM
   uint32_t* bins = (uint32_t*)(base + L.bins);
   uint32_t* bin_off = (uint32_t*)(base + L.bin_off);
   uint32_t* order = (uint32_t*)(base + L.order);
-  G1Affine* phi = (G1Affine*)(base + L.phi);
+  BigPoint* tab = (BigPoint*)(base + L.tab);
 
   if (d.nlocal == 0 || d.n == 0) {  // this rank owns no window: partial sum = infinity
     G1Xyzz* one = red[0];
@@ -785,14 +826,14 @@ cudaError_t launch_big_msm(const G1Affine* points, const Fr* scalars, const BigM
   cudaMemsetAsync(counts, 0, ((size_t)nb + 1) * 4, st);
   cudaMemsetAsync(meta, 0, 256, st);
   const int gd = (d.n + 255) / 256;
-  k_big_phi<<<gd, 256, 0, st>>>(points, d.n, phi);
+  k_big_tables<<<gd, 256, 0, st>>>(points, d.n, tab);
   k_big_digits<0><<<gd, 256, 0, st>>>(scalars, d.n, d, counts, nullptr, nullptr);
   cudaError_t se = launch_exclusive_scan(counts, nb, bsum, offsets, st, (1u << R) - 1u);
   if (se != cudaSuccess) return se;
   if (R > 0) cudaMemsetAsync(entries, 0xff, (size_t)(nent + 2) * 4, st);  // padding slots = infinity
   k_big_digits<1><<<gd, 256, 0, st>>>(scalars, d.n, d, counts, offsets, entries);
 
-  BigSrc src{points, phi, (uint32_t)d.n, entries, nullptr};
+  BigSrc src{tab, (uint32_t)d.n, entries, nullptr};
   if (R > 0) {
     G1Affine* work[2] = {(G1Affine*)(base + L.work0), (G1Affine*)(base + L.work1)};
     Fp* pre = (Fp*)(base + L.pre);
@@ -801,17 +842,22 @@ cudaError_t launch_big_msm(const G1Affine* points, const Fr* scalars, const BigM
     for (int r = 1; r <= R; r++) {
       const uint64_t npairs = nent >> r;  // upper bound; the kernels read the exact count
       if (npairs == 0) break;
-      const int bpt = ba_pairs_per_thread(npairs, sm_count);
-      const uint32_t nblk = (uint32_t)((npairs + (uint64_t)kBaThreads * bpt - 1) / ((uint64_t)kBaThreads * bpt));
+      const uint32_t nblk = ba_grid(npairs, sm_count);
       const uint32_t ntot = nblk * (uint32_t)kBaThreads;
-      int G = (int)(ntot / ((uint32_t)sm_count * 512u));
-      G = G < 1 ? 1 : G > 32 ? 32 : G;
+      // totals per inverting thread: one field inversion costs ~ 85 products, so as few threads as keep
+      // every scheduler busy (kBaInvThreadsPerSm per SM) share the totals among them
+      static const uint32_t inv_tpsm = [] {
+        const char* e = getenv("CDL_BA_INV_TPSM");
+        return e ? (uint32_t)atoi(e) : 256u;
+      }();
+      int G = (int)(ntot / ((uint32_t)sm_count * inv_tpsm));
+      G = G < 1 ? 1 : G > 256 ? 256 : G;
       G1Affine* dst = work[(r - 1) & 1];
-      if (r == 1) k_ba_fwd<false><<<nblk, kBaThreads, 0, st>>>(src, offsets + nb, r - 1, bpt, pre, totals);
-      else k_ba_fwd<true><<<nblk, kBaThreads, 0, st>>>(src, offsets + nb, r - 1, bpt, pre, totals);
+      if (r == 1) k_ba_fwd<false><<<nblk, kBaThreads, 0, st>>>(src, offsets + nb, r - 1, pre, totals);
+      else k_ba_fwd<true><<<nblk, kBaThreads, 0, st>>>(src, offsets + nb, r - 1, pre, totals);
       k_ba_inv<<<(ntot + kBaThreads * G - 1) / (kBaThreads * G), kBaThreads, 0, st>>>(totals, tpre, ntot, G);
-      if (r == 1) k_ba_bwd<false><<<nblk, kBaThreads, 0, st>>>(src, offsets + nb, r - 1, bpt, pre, totals, dst);
-      else k_ba_bwd<true><<<nblk, kBaThreads, 0, st>>>(src, offsets + nb, r - 1, bpt, pre, totals, dst);
+      if (r == 1) k_ba_bwd<false><<<nblk, kBaThreads, 0, st>>>(src, offsets + nb, r - 1, pre, totals, dst);
+      else k_ba_bwd<true><<<nblk, kBaThreads, 0, st>>>(src, offsets + nb, r - 1, pre, totals, dst);
       src.direct = dst;
     }
   }
