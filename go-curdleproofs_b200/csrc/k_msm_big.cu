@@ -682,7 +682,9 @@ int big_msm_pick_c(size_t n) {
 
 // Batch-affine rounds by the mean number of entries per bucket: a round halves every bucket at 6.3
 // instead of 10 products per addition, but pads every bucket to a multiple of 2^R slots (2^R / 2 wasted
-// pair slots on average) and costs three more launches; below ~ 32 entries per bucket it does not pay.
+// pair slots on average) and costs three more launches, one of them a field inversion's latency long;
+// below ~ 16 entries per bucket it does not pay (measured with c = 16, profiles/r3_msm_ba_scan.txt:
+// 2^17 -> 0 rounds, 2^18 -> 1, 2^19 / 2^20 -> 2, 2^21 -> 3, 2^22 -> 4).
 static int big_msm_pick_rounds(size_t mean) {
   static const int forced = [] {
     const char* e = getenv("CDL_MSM_BATCH_AFFINE");
@@ -691,7 +693,7 @@ static int big_msm_pick_rounds(size_t mean) {
   if (forced >= 0) return forced > kBigMaxBaRounds ? kBigMaxBaRounds : forced;
   int lg = 0;
   while (((size_t)2 << lg) <= mean) lg++;
-  int r = lg - 4;  // leaves 16 .. 31 points per bucket to the XYZZ pass
+  int r = lg <= 5 ? lg - 3 : lg - 4;  // leaves 8 .. 31 points per bucket to the XYZZ pass
   return r < 0 ? 0 : r > kBigMaxBaRounds ? kBigMaxBaRounds : r;
 }
 
