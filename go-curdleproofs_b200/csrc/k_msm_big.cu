@@ -461,7 +461,7 @@ k_ba_inv(Fp* __restrict__ totals, Fp* __restrict__ tpre, uint32_t ntot, int G) {
 }
 
 template <bool DIRECT>
-__global__ void __launch_bounds__(kBaThreads)
+__global__ void __launch_bounds__(kBaThreads, 4)
 k_ba_bwd(const BigSrc src, const uint32_t* __restrict__ total_ptr, int shift, const Fp* __restrict__ pre,
          const Fp* __restrict__ totals, G1Affine* __restrict__ dst) {
   const uint32_t npairs = (total_ptr[0] >> shift) >> 1;
