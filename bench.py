@@ -784,11 +784,11 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=2048, help="independent Whisk round trips per GPU per step")
+    ap.add_argument("--batch", type=int, default=4096, help="independent Whisk round trips per GPU per step")
     ap.add_argument("--batch512", type=int, default=384, help="round trips per GPU per step of the n=512 line")
     ap.add_argument("--verify-total", type=int, default=VERIFY_TOTAL, help="proofs of config 4, sharded over the ranks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--lanes", type=int, default=8, help="concurrent sub-batches per GPU (0 = library default)")
+    ap.add_argument("--lanes", type=int, default=6, help="concurrent sub-batches per GPU (0 = library default)")
     ap.add_argument("--no-msm", action="store_true", help="skip the standalone MSM sweep")
     ap.add_argument("--no-latency", action="store_true", help="skip the single-proof latency lines")
     ap.add_argument("--no-config4", action="store_true", help="skip the sharded batched-verification pass")

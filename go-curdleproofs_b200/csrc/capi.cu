@@ -28,7 +28,7 @@ static_assert(sizeof(G1Jac) == sizeof(cdl_g1_jac), "jac layout");
 
 extern "C" {
 
-uint32_t cdl_abi_version(void) { return (1u << 16) | 3u; }
+uint32_t cdl_abi_version(void) { return (1u << 16) | 4u; }
 
 int32_t cdl_create(int device, cdl_ctx** out) {
   if (!out) return CDL_ERR_INVALID_ARG;

@@ -12,10 +12,12 @@ path, batch = sys.argv[1], int(sys.argv[2])
 rows = list(csv.reader(open(path)))
 hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
 hdr, data = rows[hi], rows[hi + 1:]
-CLASS = {"k_msm_recode": "msm_small", "k_msm_warp": "msm_small", "k_msm_chunk_sum": "msm_small",
-         "k_msm_combine_tp": "msm_small", "k_msm_small": "msm_small", "k_elem_ops": "elem_scalar_mul",
+CLASS = {"k_msm_recode": "msm_small", "k_msm_warp": "msm_small", "k_msm_warp_gmem": "msm_small", "k_msm_chunk_sum": "msm_small",
+         "k_msm_combine_tp": "msm_small", "k_msm_combine_quad": "msm_small", "k_msm_small": "msm_small",
+         "k_elem_ops": "elem_scalar_mul", "k_elem_ops_quad": "elem_scalar_mul",
          "k_decompress_idx": "decompress", "k_compress_idx": "compress", "k_jac_to_affine": "compress"}
-STAGE_END = {"msm_small": ("k_msm_combine_tp", "k_msm_small"), "elem_scalar_mul": ("k_elem_ops",),
+STAGE_END = {"msm_small": ("k_msm_combine_tp", "k_msm_combine_quad", "k_msm_small"),
+             "elem_scalar_mul": ("k_elem_ops", "k_elem_ops_quad"),
              "decompress": ("k_decompress_idx",), "compress": ("k_compress_idx", "k_jac_to_affine")}
 bytes_ = defaultdict(float)
 stages = defaultdict(int)
@@ -27,10 +29,12 @@ for r in data:
     cls = CLASS.get(name)
     if not cls:
         continue
-    bytes_[cls] += float(d["Metric Value"].replace(",", "")) * unit_scale.get(d["Metric Unit"], 1)
     if name in STAGE_END[cls] and d["ID"] not in seen:
         seen.add(d["ID"])
         stages[cls] += 1
+    if "dram__bytes" not in d["Metric Name"]:
+        continue
+    bytes_[cls] += float(d["Metric Value"].replace(",", "")) * unit_scale.get(d["Metric Unit"], 1)
 out = {"batch": batch, "source": os.path.basename(path),
        "what": "dram__bytes_read.sum + dram__bytes_write.sum per class launch (ncu, lanes = 1)"}
 for cls in bytes_:
