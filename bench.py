@@ -788,13 +788,18 @@ def main():
     ap.add_argument("--batch512", type=int, default=384, help="round trips per GPU per step of the n=512 line")
     ap.add_argument("--verify-total", type=int, default=VERIFY_TOTAL, help="proofs of config 4, sharded over the ranks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--lanes", type=int, default=6, help="concurrent sub-batches per GPU (0 = library default)")
+    ap.add_argument("--lanes", type=int, default=-1,
+                    help="concurrent sub-batches per GPU (0 = library default; -1 = 6, or 8 when a rank has fewer than "
+                         "8 host cores: measured best on 16 / 4 cores per GPU)")
     ap.add_argument("--no-msm", action="store_true", help="skip the standalone MSM sweep")
     ap.add_argument("--no-latency", action="store_true", help="skip the single-proof latency lines")
     ap.add_argument("--no-config4", action="store_true", help="skip the sharded batched-verification pass")
     ap.add_argument("--no-n512", action="store_true", help="skip the n=512 throughput line")
     ap.add_argument("--msm-sizes", default="", help="comma separated log2 sizes for the MSM sweep")
     args = ap.parse_args()
+    if args.lanes < 0:
+        world_ = max(1, int(os.environ.get("WORLD_SIZE", "1")))
+        args.lanes = 6 if (os.cpu_count() or 1) // world_ >= 8 else 8
     if args.impl == "reference":
         reference_main(args)
     else:

@@ -30,7 +30,9 @@ const uint64_t kFpOne[6] = {0x760900000002fffdull, 0xebf4000bc40c0002ull, 0x5f48
 
 Engine* engine_of(cdl_ctx* c) {
   if (!c->engine) c->engine = new Engine(c);
-  return static_cast<Engine*>(c->engine);
+  Engine* E = static_cast<Engine*>(c->engine);
+  E->clear_fixed();  // begin_call selects the tables of its CRS; every other call runs without
+  return E;
 }
 
 void affine_to_jac(cdl_g1_jac* out, const cdl_g1_affine& a) {
@@ -100,6 +102,7 @@ int32_t begin_call(cdl_ctx* c, const cdl_crs* crs, size_t B, Engine** E, Layout*
   c->spin_wait = B < 8 && c->parent == nullptr;  // latency regime: see cdl_ctx::sync_stream
   int32_t rc = (*E)->ensure_pool((size_t)L->crs_size + B * (size_t)L->inst_size);
   if (rc) return rc;
+  (*E)->select_fixed(*L, crs, B);
   return (*E)->load_crs(*L, crs);
 }
 
@@ -321,6 +324,7 @@ size_t cdl_crs_ell(const cdl_crs* crs) { return crs ? crs->ell : 0; }
 void cdl_crs_free(cdl_crs* crs) {
   if (!crs) return;
   if (crs->d_points) { cudaSetDevice(crs->ctx->device); cudaFree(crs->d_points); }
+  if (crs->d_fixed) { cudaSetDevice(crs->ctx->device); cudaFree(crs->d_fixed); }
   delete crs;
 }
 

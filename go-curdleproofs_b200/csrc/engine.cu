@@ -137,6 +137,38 @@ int32_t Engine::load_crs(const Layout& L, const cdl_crs* crs) {
   return CDL_OK;
 }
 
+// Batches of at least CDL_FIXED_BASE_MINB instances (default 64 per lane; 0 = never) use fixed-base tables
+// for the CRS points.  The tables belong to the CRS object and are built on first use (~ 10 ms and
+// 4.3 MB per point); a failed allocation simply leaves the generic kernels in charge.
+void Engine::select_fixed(const Layout& L, const cdl_crs* crs, size_t B) {
+  fixed_ = cdl::FixedTable();
+  static const long min_b = [] {
+    const char* e = getenv("CDL_FIXED_BASE_MINB");
+    return e ? atol(e) : 64L;
+  }();
+  if (min_b <= 0 || (long)B < min_b) return;
+  std::lock_guard<std::mutex> lk(crs->fixed_mu);
+  if (!crs->d_fixed && !crs->fixed_failed) {
+    cdl::G1Affine* tab = nullptr;
+    if (cudaMalloc(&tab, cdl::fixed_table_bytes(L.crs_size)) != cudaSuccess) {
+      cudaGetLastError();
+      crs->fixed_failed = true;
+      return;
+    }
+    cdl::launch_fixed_build(crs->d_points, L.crs_size, tab, ctx_->stream);
+    if (cudaStreamSynchronize(ctx_->stream) != cudaSuccess) {
+      cudaFree(tab);
+      crs->fixed_failed = true;
+      return;
+    }
+    crs->d_fixed = tab;
+  }
+  if (crs->d_fixed) {
+    fixed_.tab = crs->d_fixed;
+    fixed_.nbase = L.crs_size;
+  }
+}
+
 int32_t Engine::upload_points(uint32_t dst, const void* host_affine, size_t count) {
   if (!count) return CDL_OK;
   CDL_CUDA(ctx_, cudaMemcpyAsync(d_pool_ + dst, host_affine, count * sizeof(G1Affine), cudaMemcpyHostToDevice, ctx_->stream));
@@ -246,6 +278,8 @@ int32_t Engine::decompress(const uint8_t* enc48, const std::vector<uint32_t>& ds
   return CDL_OK;
 }
 
+static constexpr uint32_t kFixedMinTerms = 16;
+
 int32_t Engine::run_msm(MsmStage& st, const std::function<int32_t(cdl::Fr* d_scalars)>& before) {
   ProfScope ps(prof.gpu);
   size_t nt = st.tasks.size(), nterm = st.idx.size();
@@ -257,11 +291,24 @@ int32_t Engine::run_msm(MsmStage& st, const std::function<int32_t(cdl::Fr* d_sca
   if ((rc = reserve(s_idx_, (nterm + 1) * 4)) || (rc = reserve(s_sc_, (nterm + 1) * 32)) ||
       (rc = reserve(s_task_, nt * sizeof(MsmTask))) || (rc = reserve(s_out_, nt * 48)))
     return rc;
+  const bool throughput = (int)nt >= cdl::kMsmSplitThreshold || max_terms > cdl::kMsmSplitTerms;
   {
     ProfScope pc(prof.copy);
     memcpy(s_idx_.h, st.idx.data(), nterm * 4);
     memcpy(s_sc_.h, st.sc.data(), nterm * 32);
     memcpy(s_task_.h, st.tasks.data(), nt * sizeof(MsmTask));
+    if (throughput && fixed_.tab) {
+      // terms on CRS points go through the fixed-base tables when their task holds enough of them to pay
+      // for the extra pass (a chunk's lanes share 22 look-ups per 32 such terms; a lone term costs as much)
+      uint32_t* idx = (uint32_t*)s_idx_.h;
+      for (const MsmTask& t : st.tasks) {
+        uint32_t cnt = 0;
+        for (uint32_t k = 0; k < t.term_cnt; k++) cnt += (idx[t.term_off + k] & 0x7fffffffu) < fixed_.nbase;
+        if (cnt < kFixedMinTerms) continue;
+        for (uint32_t k = 0; k < t.term_cnt; k++)
+          if ((idx[t.term_off + k] & 0x7fffffffu) < fixed_.nbase) idx[t.term_off + k] |= cdl::kMsmIdxFixed;
+      }
+    }
   }
   CDL_CUDA(ctx_, cudaMemcpyAsync(s_idx_.d, s_idx_.h, nterm * 4, cudaMemcpyHostToDevice, ctx_->stream));
   CDL_CUDA(ctx_, cudaMemcpyAsync(s_sc_.d, s_sc_.h, nterm * 32, cudaMemcpyHostToDevice, ctx_->stream));
@@ -272,7 +319,7 @@ int32_t Engine::run_msm(MsmStage& st, const std::function<int32_t(cdl::Fr* d_sca
   }
   double alg = 0;
   for (auto& t : st.tasks) alg += msm_algorithmic_modmul(t.term_cnt);
-  if ((int)nt >= cdl::kMsmSplitThreshold || max_terms > cdl::kMsmSplitTerms) {
+  if (throughput) {
     // throughput path: recode + warp-per-chunk + per-task combine
     std::vector<cdl::MsmSub> subs;
     std::vector<cdl::MsmTask2> tasks2;
@@ -295,7 +342,7 @@ int32_t Engine::run_msm(MsmStage& st, const std::function<int32_t(cdl::Fr* d_sca
     tick();
     cdl::launch_msm_tp(d_pool_, (const uint32_t*)s_idx_.d, (const cdl::Fr*)s_sc_.d, (int)nterm, (const cdl::MsmSub*)s_sub_.d,
                        (int)subs.size(), (const cdl::MsmTask2*)s_t2_.d, (int)nt, d_pool_, (uint8_t*)s_out_.d, d_win_,
-                       ctx_->stream);
+                       ctx_->stream, fixed_);
     tock(0, alg, 128.0 * nterm);
     launches += 3;
   } else {
@@ -325,7 +372,7 @@ int32_t Engine::run_elem(const std::vector<ElemOp>& ops, const std::vector<Fr>& 
   CDL_CUDA(ctx_, cudaMemcpyAsync(s_ops_.d, s_ops_.h, n * sizeof(ElemOp), cudaMemcpyHostToDevice, ctx_->stream));
   CDL_CUDA(ctx_, cudaMemcpyAsync(s_sc_.d, s_sc_.h, sc.size() * 32, cudaMemcpyHostToDevice, ctx_->stream));
   tick();
-  cdl::launch_elem_ops(d_pool_, (const ElemOp*)s_ops_.d, (const cdl::Fr*)s_sc_.d, (int)n, ctx_->stream);
+  cdl::launch_elem_ops(d_pool_, (const ElemOp*)s_ops_.d, (const cdl::Fr*)s_sc_.d, (int)n, ctx_->stream, fixed_);
   tock(1, 3193.0 * n, 288.0 * n);  // §8d: 3193 modmul per scalar multiplication; src + add + dst points
   CDL_CUDA(ctx_, cudaGetLastError());
   CDL_CUDA(ctx_, ctx_->sync_stream());
@@ -659,8 +706,8 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
       if (!witness_is_ours)
         for (uint32_t i = 0; i < n; i++) sl.term(base + L.Gp + i, s.ds[i]);
       sl.end();
-      sl.begin(base + L.scratch + 4);  // B_c
-      for (uint32_t i = 0; i < n; i++) sl.term(base + L.G + i, rs_c[b][i]);
+      sl.begin(base + L.scratch + 4);  // B_c: G is still the unfolded Gs || Hs, named by its CRS-image indices
+      for (uint32_t i = 0; i < n; i++) sl.term(L.Gs + i, rs_c[b][i]);  // (fixed-base tables, fixed_base.cuh)
       sl.end();
       sl.begin(base + L.scratch + 5);  // B_d
       for (uint32_t i = 0; i < n; i++) sl.term(base + L.Gp + i, rs_d[b][i]);
@@ -697,15 +744,18 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
       uint32_t base = L.base((uint32_t)b);
       const Fr *c_L = s.cs.data(), *c_R = s.cs.data() + half, *d_L = s.ds.data(), *d_R = s.ds.data() + half;
       MsmSlice sl = sb.slice((uint32_t)b);
+      // first round: G is the unfolded Gs || Hs (adjacent in the CRS image); naming the CRS points themselves
+      // lets the launch use their fixed-base tables
+      const uint32_t g0 = half == n / 2 ? L.Gs : base + L.G;
       sl.begin(base + L.scratch);  // L_C = <c_L, G_R> + <c_L, d_R> * (beta*H)
-      for (uint32_t i = 0; i < half; i++) sl.term(base + L.G + half + i, c_L[i]);
+      for (uint32_t i = 0; i < half; i++) sl.term(g0 + half + i, c_L[i]);
       sl.term(L.H, fr_mul(s.beta_ipa, fr_inner(c_L, d_R, half)));
       sl.end();
       sl.begin(base + L.scratch + 1);  // L_D = <d_R, G'_L>
       for (uint32_t i = 0; i < half; i++) sl.term(base + L.Gp + i, d_R[i]);
       sl.end();
       sl.begin(base + L.scratch + 2);  // R_C = <c_R, G_L> + <c_R, d_L> * (beta*H)
-      for (uint32_t i = 0; i < half; i++) sl.term(base + L.G + i, c_R[i]);
+      for (uint32_t i = 0; i < half; i++) sl.term(g0 + i, c_R[i]);
       sl.term(L.H, fr_mul(s.beta_ipa, fr_inner(c_R, d_L, half)));
       sl.end();
       sl.begin(base + L.scratch + 3);  // R_D = <d_L, G'_R>
@@ -738,8 +788,9 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
       if (half > 1) {  // the folded bases of the last round are never read again
         uint32_t base = L.base((uint32_t)b);
         ElemOp* o = ops.data() + b * 2 * half;
+        const uint32_t g0 = half == n / 2 ? L.Gs : base + L.G;  // first fold: sources are the CRS points
         for (uint32_t i = 0; i < half; i++) {
-          o[i] = ElemOp{base + L.G + half + i, base + L.G + i, base + L.G + i, (uint32_t)(2 * b)};
+          o[i] = ElemOp{g0 + half + i, g0 + i, base + L.G + i, (uint32_t)(2 * b)};
           o[half + i] = ElemOp{base + L.Gp + half + i, base + L.Gp + i, base + L.Gp + i, (uint32_t)(2 * b + 1)};
         }
       }
@@ -811,7 +862,7 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
       sl.term(base + L.A, FR_ONE); sl.term(L.Gt, s.r_t); sl.term(L.Gu, s.r_u);
       sl.end();
       sl.begin(o + 11);                              // B_a = <r, G>
-      for (uint32_t i = 0; i < n; i++) sl.term(base + L.Gm + i, s.r[i]);
+      for (uint32_t i = 0; i < n; i++) sl.term(i < ell + 2 ? L.Gs + i : L.Gt + (i - ell - 2), s.r[i]);  // Gm = Gs || Hs[0..2) || Gt || Gu
       sl.end();
       sl.begin(o + 12);                              // B_t = <r, T'>
       for (uint32_t i = 0; i < ell; i++) sl.term(base + L.Ts + i, s.r[i]);
@@ -892,14 +943,20 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
       const Fr *x_L = s.x.data(), *x_R = s.x.data() + half;
       MsmSlice sl = sb.slice((uint32_t)b);
       const uint32_t vec[3] = {L.Gm, L.Tp, L.Up};
+      // first round: Gm is still Gs || Hs[0..2) || Gt || Gu, named by its CRS-image indices (fixed-base tables)
+      const bool first = half == n / 2;
+      auto pt = [&](int v, uint32_t i) {
+        if (v == 0 && first) return i < ell + 2 ? L.Gs + i : L.Gt + (i - ell - 2);
+        return base + vec[v] + i;
+      };
       for (int v = 0; v < 3; v++) {  // L_A, L_T, L_U over the right halves with x_L
         sl.begin(base + L.scratch + v);
-        for (uint32_t i = 0; i < half; i++) sl.term(base + vec[v] + half + i, x_L[i]);
+        for (uint32_t i = 0; i < half; i++) sl.term(pt(v, half + i), x_L[i]);
         sl.end();
       }
       for (int v = 0; v < 3; v++) {  // R_A, R_T, R_U over the left halves with x_R
         sl.begin(base + L.scratch + 3 + v);
-        for (uint32_t i = 0; i < half; i++) sl.term(base + vec[v] + i, x_R[i]);
+        for (uint32_t i = 0; i < half; i++) sl.term(pt(v, i), x_R[i]);
         sl.end();
       }
     });
@@ -922,10 +979,17 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
       if (half > 1) {
         uint32_t base = L.base((uint32_t)b);
         const uint32_t vec[3] = {L.Tp, L.Up, L.Gm};
+        const bool first = half == n / 2;  // first fold of Gm: sources are the CRS points
         ElemOp* o = ops.data() + b * 3 * half;
         for (int v = 0; v < 3; v++)
-          for (uint32_t i = 0; i < half; i++)
-            o[v * half + i] = ElemOp{base + vec[v] + half + i, base + vec[v] + i, base + vec[v] + i, (uint32_t)b};
+          for (uint32_t i = 0; i < half; i++) {
+            uint32_t src = base + vec[v] + half + i, add = base + vec[v] + i;
+            if (v == 2 && first) {
+              src = half + i < ell + 2 ? L.Gs + half + i : L.Gt + (half + i - ell - 2);
+              add = L.Gs + i;  // i < half <= ell + 2
+            }
+            o[v * half + i] = ElemOp{src, add, base + vec[v] + i, (uint32_t)b};
+          }
       }
     });
     if ((rc = run_elem(ops, sc))) return rc;

@@ -34,6 +34,10 @@ struct cdl_crs {
   uint32_t ell = 0;
   cdl::G1Affine* d_points = nullptr;  // Gs[ell] Hs[4] H Gt Gu Gsum Hsum INF  (ell + 10 points)
   std::vector<uint8_t> enc;           // same order, 48 B each
+  // fixed-base tables of those points (csrc/fixed_base.cuh), built by the first large batch that uses this CRS
+  mutable std::mutex fixed_mu;
+  mutable cdl::G1Affine* d_fixed = nullptr;
+  mutable bool fixed_failed = false;
 };
 
 namespace cdlh {
@@ -120,6 +124,9 @@ class Engine {
   // --- pool plumbing ----------------------------------------------------------
   int32_t ensure_pool(size_t npoints);
   int32_t load_crs(const Layout& L, const cdl_crs* crs);
+  // fixed-base tables for this call's CRS image (pool indices below crs_size); B = instances of the call
+  void select_fixed(const Layout& L, const cdl_crs* crs, size_t B);
+  void clear_fixed() { fixed_ = cdl::FixedTable(); }  // calls whose pool does not start with a CRS image
   int32_t upload_points(uint32_t dst, const void* host_affine, size_t count);
   int32_t upload_jac(uint32_t dst, const void* host_jac, size_t count);  // normalises to affine on the device
   int32_t download_points(uint32_t src, void* host_affine, size_t count);
@@ -179,6 +186,7 @@ class Engine {
   cdl_ctx* ctx_;
   ThreadPool pool_;
   cdl::G1Affine* d_pool_ = nullptr;
+  cdl::FixedTable fixed_;  // tables of the current call's CRS, or empty
   size_t pool_cap_ = 0;
   void* d_win_ = nullptr;  // window sums of the two-kernel MSM path
   size_t win_cap_ = 0;

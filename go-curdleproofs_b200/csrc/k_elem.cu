@@ -23,7 +23,7 @@ constexpr int kEB = 8;
 #endif
 
 template <class Load, class Store>
-__device__ __forceinline__ void scalar_mul_batched(int n, Load load, Store store) {
+__device__ __forceinline__ void scalar_mul_batched(int n, const FixedTable& ft, Load load, Store store) {
   const int T = gridDim.x * blockDim.x;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   G1Jac res[kEB];  // local memory (indexed in rolled loops): 144 B per pending point
@@ -40,10 +40,18 @@ __device__ __forceinline__ void scalar_mul_batched(int n, Load load, Store store
       G1Affine p, l;
       Fr km, k;
       bool has_add;
-      load(i, p, km, l, has_add);
+      int fb = -1;  // index of a tabulated base (fixed_base.cuh), or -1
+      load(i, p, km, l, has_add, fb);
       FrM::from_mont(k, km);
       G1Jac r;
-      jac_scalar_mul_glv(r, p, k.v);
+      if (fb >= 0) {  // uniform across a warp in practice: a stage's ops are all on CRS points or none is
+        G1Xyzz x;
+        xyzz_set_inf(x);
+        fixed_base_accumulate<false>(x, ft, (uint32_t)fb, k.v, false);
+        xyzz_to_jac(r, x);
+      } else {
+        jac_scalar_mul_glv(r, p, k.v);
+      }
       if (has_add) jac_add_mixed(r, r, l);
       if (!jac_is_inf(r)) FpM::mul(run, run, r.z);
       res[e] = r;
@@ -73,8 +81,9 @@ __global__ void __launch_bounds__(64, CDL_ELEM_MINB)
 k_scalar_mul(const G1Affine* __restrict__ P, const Fr* __restrict__ s, int stride,
              const G1Affine* __restrict__ L, G1Affine* __restrict__ out, int n) {
   scalar_mul_batched(
-      n,
-      [&](int i, G1Affine& p, Fr& km, G1Affine& l, bool& has_add) {
+      n, FixedTable(),
+      [&](int i, G1Affine& p, Fr& km, G1Affine& l, bool& has_add, int& fb) {
+        (void)fb;
         km = s[(size_t)i * stride];
         p = P[i];
         has_add = L != nullptr;
@@ -141,12 +150,14 @@ k_jac_to_affine(const G1Jac* __restrict__ in, G1Affine* __restrict__ out, int n)
 // + 1/kEB inversion per point.  The persistent grid also removes the tail of the last wave: every
 // thread of a launch does floor or ceil of n / T equal-cost items.
 __global__ void __launch_bounds__(64, CDL_ELEM_MINB)
-k_elem_ops(G1Affine* __restrict__ pool, const ElemOp* __restrict__ ops, const Fr* __restrict__ scalars, int n) {
+k_elem_ops(G1Affine* __restrict__ pool, const ElemOp* __restrict__ ops, const Fr* __restrict__ scalars, int n,
+           const FixedTable ft) {
   scalar_mul_batched(
-      n,
-      [&](int i, G1Affine& p, Fr& km, G1Affine& l, bool& has_add) {
+      n, ft,
+      [&](int i, G1Affine& p, Fr& km, G1Affine& l, bool& has_add, int& fb) {
         const ElemOp op = ops[i];
         km = scalars[op.sc];
+        if (op.src < ft.nbase) fb = (int)op.src;
         p = pool[op.src];
         has_add = op.add != kNoPoint;
         if (has_add) l = pool[op.add];
@@ -231,7 +242,7 @@ static int balanced_blocks(int n, int tpb, int resident) {
   return (threads + tpb - 1) / tpb;
 }
 
-void launch_elem_ops(G1Affine* pool, const ElemOp* ops, const Fr* scalars, int n, cudaStream_t st) {
+void launch_elem_ops(G1Affine* pool, const ElemOp* ops, const Fr* scalars, int n, cudaStream_t st, FixedTable ft) {
   if (n <= 0) return;
   if (n <= kQuadMaxOps) {
     k_elem_ops_quad<<<(n + kQuadOpsPerCta - 1) / kQuadOpsPerCta, 4 * kQuadOpsPerCta, 0, st>>>(pool, ops, scalars, n);
@@ -240,7 +251,8 @@ void launch_elem_ops(G1Affine* pool, const ElemOp* ops, const Fr* scalars, int n
   const int tpb = 64;
   static thread_local int resident = 0;  // one device per context thread; re-queried per thread
   if (!resident) resident = resident_ctas(k_elem_ops, tpb);
-  k_elem_ops<<<balanced_blocks(n, tpb, resident), tpb, 0, st>>>(pool, ops, scalars, n);
+  if (!ft.tab) ft.nbase = 0;
+  k_elem_ops<<<balanced_blocks(n, tpb, resident), tpb, 0, st>>>(pool, ops, scalars, n, ft);
 }
 
 void launch_scalar_mul(const G1Affine* P, const Fr* s, int stride, const G1Affine* L, G1Affine* out, int n,

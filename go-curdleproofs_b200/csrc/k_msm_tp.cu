@@ -30,6 +30,8 @@
 namespace cdl {
 
 constexpr int kTpWindows = 32;
+constexpr int kTpRows = kTpWindows + 1;  // rows of the window-sum arrays: 32 windows + the chunk's fixed-base sum (weight 1)
+constexpr uint32_t kIdxFixed = kMsmIdxFixed;  // term index flag set by the host: sum this term from the fixed-base tables
 
 // Streaming (evict-first) loads for data a warp reads once — the recoded terms and the base
 // points — so that they do not push the warps' bucket arrays (local memory, re-read on every
@@ -59,14 +61,15 @@ struct alignas(16) MsmRec {
   uint32_t k1p[4];
   uint32_t k2p[4];
   uint32_t pidx;   // pool index of the base
-  uint32_t flags;  // bit 0: negate the P part, bit 1: negate the phi(P) part, bit 2: the base is the point at infinity
+  uint32_t flags;  // bit 0: negate the P part, bit 1: negate the phi(P) part, bit 2: the base is the point at infinity,
+                   // bit 3: fixed-base term (summed from the tables by k_msm_fixed; bucket warps skip it), bit 4: negate it
   uint32_t pad[2];
   Fp bx;           // beta * x of the base: the x coordinate of phi(P), computed once per term here
                    // instead of once per term by all 32 lanes of the bucket warp
 };
 
 __global__ void k_msm_recode(const G1Affine* __restrict__ points, const uint32_t* __restrict__ idx,
-                             const Fr* __restrict__ scalars, MsmRec* __restrict__ rec, int nterm) {
+                             const Fr* __restrict__ scalars, MsmRec* __restrict__ rec, int nterm, uint32_t nfixed) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nterm) return;
   Fr km = scalars[t], k;
@@ -76,10 +79,12 @@ __global__ void k_msm_recode(const G1Affine* __restrict__ points, const uint32_t
   MsmRec r;
   glv_bias(r.k1p, g.k1);
   glv_bias(r.k2p, g.k2);
-  r.pidx = idx[t] & 0x7fffffffu;
+  r.pidx = idx[t] & 0x3fffffffu;
   bool flip = (idx[t] >> 31) != 0;
+  const bool fixed_term = (idx[t] & kIdxFixed) != 0 && r.pidx < nfixed;
   const G1Affine base = points[r.pidx];
-  r.flags = ((g.neg1 != flip) ? 1u : 0u) | ((g.neg2 != flip) ? 2u : 0u) | (aff_is_inf(base) ? 4u : 0u);
+  r.flags = ((g.neg1 != flip) ? 1u : 0u) | ((g.neg2 != flip) ? 2u : 0u) | (aff_is_inf(base) ? 4u : 0u) |
+            (fixed_term ? 8u : 0u) | (flip ? 16u : 0u);
   r.pad[0] = r.pad[1] = 0;
   Fp beta;
   fp_set_beta(beta);
@@ -123,7 +128,7 @@ k_msm_warp_gmem(const G1Affine* __restrict__ points, const MsmRec* __restrict__ 
       const uint4 k1 = __ldcs(reinterpret_cast<const uint4*>(rp->k1p));
       const uint4 k2 = __ldcs(reinterpret_cast<const uint4*>(rp->k2p));
       const uint2 pf = __ldcs(reinterpret_cast<const uint2*>(&rp->pidx));  // pidx, flags
-      if (pf.y & 4u) continue;  // base at infinity (uniform across the warp)
+      if (pf.y & 12u) continue;  // base at infinity, or a fixed-base term (uniform across the warp)
 #pragma unroll 1
       for (int h = 0; h < 2; h++) {
         const uint4 kk = h == 0 ? k1 : k2;
@@ -218,13 +223,57 @@ void msm_l2_carveout(bool on) {
 
 static size_t bucket_scratch_bytes(int sms) { return (size_t)sms * kCtasPerSm * kWarpsPerCta * kWarpBucketBytes; }
 
+// Fixed-base terms (fixed_base.cuh): one warp per chunk, lane l takes the chunk's terms l, l + 32, ..; a
+// term flagged by the host (kIdxFixed: its task holds enough terms on tabulated points to pay for the
+// pass) is 22 table look-ups and mixed additions, no doublings, no buckets.  The lanes' sums are added
+// up with a shuffle tree into row 32 of the chunk's window sums, which k_msm_chunk_sum and
+// k_msm_combine_* carry along with weight 1.
+__global__ void __launch_bounds__(128)
+k_msm_fixed(const MsmRec* __restrict__ rec, const Fr* __restrict__ scalars, const MsmSub* __restrict__ subs, int nsub,
+            FixedTable ft, G1Jac* __restrict__ win) {
+  const int sub = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (sub >= nsub) return;  // the whole warp
+  const int lane = threadIdx.x & 31;
+  const MsmSub s = subs[sub];
+  G1Xyzz acc;
+  xyzz_set_inf(acc);
+#pragma unroll 1
+  for (uint32_t t = s.term_off + (uint32_t)lane; t < s.term_off + s.term_cnt; t += 32) {
+    const uint2 pf = *reinterpret_cast<const uint2*>(&rec[t].pidx);
+    if ((pf.y & 12u) != 8u) continue;
+    Fr k;
+    FrM::from_mont(k, scalars[t]);
+    fixed_base_accumulate(acc, ft, pf.x, k.v, (pf.y & 16u) != 0);
+  }
+  G1Jac* out = win + (size_t)kTpWindows * nsub + sub;
+  // sum over the lanes (any lane may hold infinity)
+  if (!__any_sync(0xffffffffu, !xyzz_is_inf(acc))) {
+    if (lane == 0) { G1Jac z; jac_set_inf(z); *out = z; }
+    return;
+  }
+#pragma unroll 1
+  for (int off = 16; off >= 1; off >>= 1) {
+    G1Xyzz o;
+    uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+    const uint32_t* aw = reinterpret_cast<const uint32_t*>(&acc);
+#pragma unroll
+    for (int i = 0; i < 48; i++) ow[i] = __shfl_down_sync(0xffffffffu, aw[i], off);
+    if (lane < off) xyzz_add(acc, acc, o);
+  }
+  if (lane == 0) {
+    G1Jac r;
+    xyzz_to_jac(r, acc);
+    *out = r;
+  }
+}
+
 // thread per (task, window): sum of the task's chunk partials, so that the serial Horner
 // chain of k_msm_combine_tp sees one point per window however finely a task was cut
 __global__ void __launch_bounds__(128)
-k_msm_chunk_sum(const G1Jac* __restrict__ win, const MsmTask2* __restrict__ tasks, int ntasks, int nsub,
+k_msm_chunk_sum(const G1Jac* __restrict__ win, const MsmTask2* __restrict__ tasks, int ntasks, int nsub, int nrows,
                 G1Jac* __restrict__ wsum) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= ntasks * kTpWindows) return;
+  if (t >= ntasks * nrows) return;
   const int w = t / ntasks, j = t - w * ntasks;
   const MsmTask2 task = tasks[j];
   G1Jac acc;
@@ -239,7 +288,7 @@ k_msm_chunk_sum(const G1Jac* __restrict__ win, const MsmTask2* __restrict__ task
 
 __global__ void __launch_bounds__(64)
 k_msm_combine_tp(const G1Jac* __restrict__ wsum, const MsmTask2* __restrict__ tasks, int ntasks,
-                 G1Affine* __restrict__ out_aff, uint8_t* __restrict__ out_c48) {
+                 int has_fixed, G1Affine* __restrict__ out_aff, uint8_t* __restrict__ out_c48) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= ntasks) return;
   const MsmTask2 task = tasks[j];
@@ -254,17 +303,37 @@ k_msm_combine_tp(const G1Jac* __restrict__ wsum, const MsmTask2* __restrict__ ta
     G1Jac s = wsum[(size_t)w * ntasks + j];
     jac_add(acc, acc, s);
   }
+  if (has_fixed) {  // the task's fixed-base terms (k_msm_fixed), row 32
+    G1Jac f = wsum[(size_t)kTpWindows * ntasks + j];
+    jac_add(acc, acc, f);
+  }
   G1Affine a;
   jac_to_affine(a, acc);
   if (out_aff) out_aff[task.out_idx] = a;
   if (out_c48) g1_compress_dev(out_c48 + 48 * (size_t)j, a);
 }
 
+// acc += s for a Jacobian s (Jacobian -> XYZZ: ZZ = Z^2, ZZZ = Z^3), one quad per point
+__device__ __forceinline__ void quad_add_jac(const Quad& q, G1Xyzz& acc, const G1Jac& s) {
+  if (jac_is_inf(s)) return;
+  G1Xyzz sx;
+  Fp a[4], b[4], o[4];
+  a[0] = s.z; b[0] = s.z;
+  qmul<1>(q, o, a, b);
+  sx.zz = o[0];
+  a[0] = o[0]; b[0] = s.z;
+  qmul<1>(q, o, a, b);
+  sx.zzz = o[0];
+  sx.x = s.x;
+  sx.y = s.y;
+  qxyzz_add(q, acc, acc, sx);
+}
+
 // The same Horner walk with a QUAD of lanes per task (quad.cuh) for launches with few tasks (one proof
 // at a time): 124 x 3 + 32 x 4 product latencies instead of 124 x 7 + 32 x 16.
 __global__ void __launch_bounds__(32)
 k_msm_combine_quad(const G1Jac* __restrict__ wsum, const MsmTask2* __restrict__ tasks, int ntasks,
-                   G1Affine* __restrict__ out_aff, uint8_t* __restrict__ out_c48) {
+                   int has_fixed, G1Affine* __restrict__ out_aff, uint8_t* __restrict__ out_c48) {
   const Quad q;
   const int j = blockIdx.x * 8 + (threadIdx.x >> 2);
   if (j >= ntasks) return;  // the whole quad
@@ -278,19 +347,11 @@ k_msm_combine_quad(const G1Jac* __restrict__ wsum, const MsmTask2* __restrict__ 
       for (int i = 0; i < 4; i++) qxyzz_dbl(q, acc, acc);
     }
     const G1Jac s = wsum[(size_t)w * ntasks + j];
-    if (!jac_is_inf(s)) {  // Jacobian -> XYZZ: ZZ = Z^2, ZZZ = Z^3
-      G1Xyzz sx;
-      Fp a[4], b[4], o[4];
-      a[0] = s.z; b[0] = s.z;
-      qmul<1>(q, o, a, b);
-      sx.zz = o[0];
-      a[0] = o[0]; b[0] = s.z;
-      qmul<1>(q, o, a, b);
-      sx.zzz = o[0];
-      sx.x = s.x;
-      sx.y = s.y;
-      qxyzz_add(q, acc, acc, sx);
-    }
+    quad_add_jac(q, acc, s);
+  }
+  if (has_fixed) {  // the task's fixed-base terms (k_msm_fixed), row 32
+    const G1Jac f = wsum[(size_t)kTpWindows * ntasks + j];
+    quad_add_jac(q, acc, f);
   }
   G1Affine a;
   qxyzz_to_affine(q, a, acc);
@@ -301,14 +362,14 @@ k_msm_combine_quad(const G1Jac* __restrict__ wsum, const MsmTask2* __restrict__ 
 }
 constexpr int kCombineQuadMaxTasks = 4096;  // above this the thread-per-task kernel has enough warps (measured: no difference from 4 096 up)
 
-// [work counter | recoded terms | chunk window sums | task window sums | bucket scratch]
+// [work counter | recoded terms | chunk window sums | task window sums | bucket scratch]; the sums have 33 rows
 size_t msm_tp_scratch_bytes(size_t nterm, size_t nsub, size_t ntasks) {
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   size_t rec = (nterm * sizeof(MsmRec) + 255) & ~(size_t)255;
-  size_t win = (nsub * kTpWindows * sizeof(G1Jac) + 255) & ~(size_t)255;
-  size_t ws = (ntasks * kTpWindows * sizeof(G1Jac) + 255) & ~(size_t)255;
+  size_t win = (nsub * kTpRows * sizeof(G1Jac) + 255) & ~(size_t)255;
+  size_t ws = (ntasks * kTpRows * sizeof(G1Jac) + 255) & ~(size_t)255;
   return 256 + rec + win + ws + bucket_scratch_bytes(sms);
 }
 
@@ -332,7 +393,7 @@ uint32_t msm_tp_pick_chunk(size_t nterm, int sm_count) {
 
 void launch_msm_tp(const G1Affine* points, const uint32_t* idx, const Fr* scalars, int nterm, const MsmSub* subs,
                    int nsub, const MsmTask2* tasks, int ntasks, G1Affine* out_aff, uint8_t* out_c48, void* scratch,
-                   cudaStream_t st) {
+                   cudaStream_t st, FixedTable ft) {
   int dev = 0;
   cudaGetDevice(&dev);
   L2Persist g;
@@ -343,12 +404,16 @@ void launch_msm_tp(const G1Affine* points, const uint32_t* idx, const Fr* scalar
   uint32_t* next = (uint32_t*)scratch;
   MsmRec* rec = (MsmRec*)((uint8_t*)scratch + 256);
   size_t rec_bytes = ((size_t)nterm * sizeof(MsmRec) + 255) & ~(size_t)255;
-  size_t win_bytes = ((size_t)nsub * kTpWindows * sizeof(G1Jac) + 255) & ~(size_t)255;
-  size_t ws_bytes = ((size_t)ntasks * kTpWindows * sizeof(G1Jac) + 255) & ~(size_t)255;
+  size_t win_bytes = ((size_t)nsub * kTpRows * sizeof(G1Jac) + 255) & ~(size_t)255;
+  size_t ws_bytes = ((size_t)ntasks * kTpRows * sizeof(G1Jac) + 255) & ~(size_t)255;
   G1Jac* win = (G1Jac*)((uint8_t*)rec + rec_bytes);
   G1Jac* wsum = (G1Jac*)((uint8_t*)win + win_bytes);
   uint4* buckets = (uint4*)((uint8_t*)wsum + ws_bytes);
-  if (nterm > 0) k_msm_recode<<<(nterm + 127) / 128, 128, 0, st>>>(points, idx, scalars, rec, nterm);
+  const bool fixed = ft.tab != nullptr && ft.nbase > 0;
+  if (nterm > 0)
+    k_msm_recode<<<(nterm + 127) / 128, 128, 0, st>>>(points, idx, scalars, rec, nterm, fixed ? ft.nbase : 0u);
+  if (fixed && nsub > 0) k_msm_fixed<<<(nsub + 3) / 4, 128, 0, st>>>(rec, scalars, subs, nsub, ft, win);
+  const int nrows = fixed ? kTpRows : kTpWindows;
   if (nsub > 0) {
     cudaMemsetAsync(next, 0, 4, st);
     if (g.bytes) {  // keep the bucket scratch resident in L2: persisting carve-out + access-policy window
@@ -364,13 +429,14 @@ void launch_msm_tp(const G1Affine* points, const uint32_t* idx, const Fr* scalar
     const int ctas = std::min((nsub + kWarpsPerCta - 1) / kWarpsPerCta, g.sms * kCtasPerSm);
     k_msm_warp_gmem<<<ctas, 32 * kWarpsPerCta, 0, st>>>(points, rec, subs, nsub, win, buckets, next);
   }
-  k_msm_chunk_sum<<<(ntasks * kTpWindows + 127) / 128, 128, 0, st>>>(win, tasks, ntasks, nsub, wsum);
+  k_msm_chunk_sum<<<(ntasks * nrows + 127) / 128, 128, 0, st>>>(win, tasks, ntasks, nsub, nrows, wsum);
   static const int quad_max = [] {
     const char* e = getenv("CDL_COMBINE_QUAD_MAX");
     return e ? atoi(e) : kCombineQuadMaxTasks;
   }();
-  if (ntasks <= quad_max) k_msm_combine_quad<<<(ntasks + 7) / 8, 32, 0, st>>>(wsum, tasks, ntasks, out_aff, out_c48);
-  else k_msm_combine_tp<<<(ntasks + 63) / 64, 64, 0, st>>>(wsum, tasks, ntasks, out_aff, out_c48);
+  const int fs = fixed ? 1 : 0;
+  if (ntasks <= quad_max) k_msm_combine_quad<<<(ntasks + 7) / 8, 32, 0, st>>>(wsum, tasks, ntasks, fs, out_aff, out_c48);
+  else k_msm_combine_tp<<<(ntasks + 63) / 64, 64, 0, st>>>(wsum, tasks, ntasks, fs, out_aff, out_c48);
 }
 
 }  // namespace cdl

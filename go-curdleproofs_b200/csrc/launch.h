@@ -5,6 +5,7 @@
 #include <cstddef>
 #include <cstdint>
 #include "g1.cuh"
+#include "fixed_base.cuh"
 
 namespace cdl {
 
@@ -35,7 +36,12 @@ void launch_peak(int kind, void* out, int blocks, int tpb, int iters, uint32_t s
 void launch_scalar_mul(const G1Affine* P, const Fr* s, int stride, const G1Affine* L, G1Affine* out, int n,
                        cudaStream_t st);
 void launch_jac_to_affine(const G1Jac* in, G1Affine* out, int n, cudaStream_t st);
-void launch_elem_ops(G1Affine* pool, const ElemOp* ops, const Fr* scalars, int n, cudaStream_t st);
+// ft: fixed-base tables of the pool's first ft.nbase points (fixed_base.cuh); ops on those sources skip the
+// double-and-add (the thread-per-op kernel only; small launches take the quad kernel)
+void launch_elem_ops(G1Affine* pool, const ElemOp* ops, const Fr* scalars, int n, cudaStream_t st,
+                     FixedTable ft = FixedTable());
+size_t fixed_table_bytes(uint32_t nbase);
+void launch_fixed_build(const G1Affine* bases, uint32_t nbase, G1Affine* tab, cudaStream_t st);
 void launch_copy_ranges(G1Affine* pool, const CopyRange* ranges, int n, cudaStream_t st);
 // verifier scalar pipeline on the device (k_verify_scalars.cu): per-proof inputs, all Montgomery fr.Element
 constexpr int kVsMaxM = 16;  // rounds (n <= 2^16)
@@ -62,13 +68,16 @@ struct MsmSub {
 struct MsmTask2 {
   uint32_t sub_off, sub_cnt, out_idx, pad;
 };
+constexpr uint32_t kMsmIdxFixed = 1u << 30;  // idx[] flag (throughput path only): sum this term from the fixed-base tables
 constexpr uint32_t kMsmChunk = 128;  // terms per bucket warp (msm_tp_pick_chunk)
 size_t msm_tp_scratch_bytes(size_t nterm, size_t nsub, size_t ntasks);
 uint32_t msm_tp_pick_chunk(size_t nterm, int sm_count);
 void msm_l2_carveout(bool on);  // persisting-L2 window of the bucket scratch: held by the batched path only
+// ft: terms on the pool's first ft.nbase points are summed from the fixed-base tables by one warp per task
+// (k_msm_fixed) and skipped by the bucket warps
 void launch_msm_tp(const G1Affine* points, const uint32_t* idx, const Fr* scalars, int nterm, const MsmSub* subs,
                    int nsub, const MsmTask2* tasks, int ntasks, G1Affine* out_aff, uint8_t* out_c48, void* scratch,
-                   cudaStream_t st);
+                   cudaStream_t st, FixedTable ft = FixedTable());
 // host helper: cut tasks into subs
 template <class VecSub, class VecTask2>
 inline void msm_build_subs(const MsmTask* tasks, size_t ntasks, uint32_t chunk, VecSub& subs, VecTask2& tasks2) {

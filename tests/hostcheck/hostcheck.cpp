@@ -5,6 +5,8 @@
 #include <cstring>
 #include "../../go-curdleproofs_b200/csrc/g1.cuh"
 #include "../../go-curdleproofs_b200/csrc/batch_affine.cuh"
+#include "../../go-curdleproofs_b200/csrc/fixed_base.cuh"
+#include <vector>
 
 using namespace cdl;
 
@@ -84,6 +86,39 @@ void hc_g1_in_subgroup(const G1Affine* p, int* out, int n) {
 }
 
 int hc_on_curve(const G1Affine* p) { return aff_on_curve(*p); }
+
+// r[i] = (neg[i] ? -k[i] : k[i]) * p through a fixed-base table of p built here the way k_fixed_build
+// (csrc/k_fixed.cu) builds it — row w holds d * 2^(12 w) * p for d = 1 .. 2048 — and read by the product's
+// own fixed_base_accumulate (csrc/fixed_base.cuh).  k: canonical little-endian 8 x u32.
+void hc_fixed_base(const G1Affine* p, const uint32_t* k, const int* neg, G1Affine* r, int n) {
+  std::vector<G1Affine> tab((size_t)kFbW * kFbM);
+  G1Jac q;
+  jac_from_affine(q, *p);
+  for (int w = 0; w < kFbW; w++) {
+    G1Affine qa;
+    jac_to_affine(qa, q);
+    G1Xyzz acc;
+    xyzz_set_inf(acc);
+    for (int d = 0; d < kFbM; d++) {
+      xyzz_add_mixed(acc, acc, qa);
+      G1Jac j;
+      xyzz_to_jac(j, acc);
+      jac_to_affine(tab[(size_t)w * kFbM + d], j);
+    }
+    for (int i = 0; i < kFbC; i++) jac_dbl(q, q);
+  }
+  FixedTable ft;
+  ft.tab = tab.data();
+  ft.nbase = 1;
+  for (int i = 0; i < n; i++) {
+    G1Xyzz acc;
+    xyzz_set_inf(acc);
+    fixed_base_accumulate(acc, ft, 0, k + 8 * i, neg[i] != 0);
+    G1Jac j;
+    xyzz_to_jac(j, acc);
+    jac_to_affine(r[i], j);
+  }
+}
 
 // r[i] = a[i] + b[i] as ONE batch-affine run (forward products, one inversion, backward peel): the
 // per-thread schedule of k_ba_fwd / k_ba_bwd (csrc/k_msm_big.cu) on the host

@@ -210,3 +210,22 @@ def test_batch_affine_run_all_cases(hc):
         hc.hc_batch_affine(b"".join(aff_enc(p) for p in A), b"".join(aff_enc(p) for p in Bv), out, pre, len(A))
         got = [aff_dec(out.raw[i * 96:(i + 1) * 96]) for i in range(len(A))]
         assert got == [b.g1_add(x, y) for x, y in zip(A, Bv)]
+
+
+def test_fixed_base_table_lookup(hc):
+    """k * P from a fixed-base table (csrc/fixed_base.cuh: signed 12-bit digits, 22 look-ups, no doublings)
+    against the oracle, on scalars that stress the digit recoding: all-ones windows (carries ripple through
+    every window), digits exactly 2048 / 2049, r - 1, single bits at window boundaries, zero."""
+    random.seed(23)
+    pt = b.g1_mul(b.G1_GEN, 0x1234567)
+    ks = [0, 1, 2047, 2048, 2049, 4095, 4096, 4097, (1 << 12) - 1, (1 << 252) - 1, R - 1, R - 2, (R - 1) // 2,
+          int("800" * 21, 16), int("801" * 21, 16), int("7ff" * 21, 16), int("fff" * 21, 16) % R, 1 << 252,
+          (1 << 254) + (1 << 11), (7 << 252) | ((1 << 252) - 1) if ((7 << 252) | ((1 << 252) - 1)) < R else R - 3]
+    ks += [1 << (12 * w) for w in range(22) if (1 << (12 * w)) < R] + [random.randrange(R) for _ in range(40)]
+    negs = [i % 3 == 0 for i in range(len(ks))]
+    out = ctypes.create_string_buffer(96 * len(ks))
+    kb = b"".join(k.to_bytes(32, "little") for k in ks)
+    hc.hc_fixed_base(aff_enc(pt), kb, (ctypes.c_int * len(ks))(*[int(x) for x in negs]), out, len(ks))
+    got = [aff_dec(out.raw[i * 96:(i + 1) * 96]) for i in range(len(ks))]
+    want = [b.g1_mul(pt, (R - k) % R if ng else k) for k, ng in zip(ks, negs)]
+    assert got == want
