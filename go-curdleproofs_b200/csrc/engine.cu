@@ -67,7 +67,7 @@ Engine::~Engine() {
   cudaSetDevice(ctx_->device);
   if (d_pool_) cudaFree(d_pool_);
   if (d_win_) cudaFree(d_win_);
-  for (Staging* s : {&s_idx_, &s_sc_, &s_task_, &s_out_, &s_ops_, &s_enc_, &s_st_, &s_jac_, &s_sub_, &s_t2_, &s_cr_, &s_vs_, &s_as_}) {
+  for (Staging* s : {&s_idx_, &s_sc_, &s_task_, &s_out_, &s_ops_, &s_enc_, &s_st_, &s_jac_, &s_sub_, &s_t2_, &s_cr_, &s_vs_, &s_as_, &s_fsub_}) {
     if (s->h) cudaFreeHost(s->h);
     if (s->d) cudaFree(s->d);
   }
@@ -292,6 +292,7 @@ int32_t Engine::run_msm(MsmStage& st, const std::function<int32_t(cdl::Fr* d_sca
       (rc = reserve(s_task_, nt * sizeof(MsmTask))) || (rc = reserve(s_out_, nt * 48)))
     return rc;
   const bool throughput = (int)nt >= cdl::kMsmSplitThreshold || max_terms > cdl::kMsmSplitTerms;
+  std::vector<uint32_t> fixed_tasks;  // tasks whose CRS terms go through the fixed-base tables
   {
     ProfScope pc(prof.copy);
     memcpy(s_idx_.h, st.idx.data(), nterm * 4);
@@ -301,12 +302,14 @@ int32_t Engine::run_msm(MsmStage& st, const std::function<int32_t(cdl::Fr* d_sca
       // terms on CRS points go through the fixed-base tables when their task holds enough of them to pay
       // for the extra pass (a chunk's lanes share 22 look-ups per 32 such terms; a lone term costs as much)
       uint32_t* idx = (uint32_t*)s_idx_.h;
-      for (const MsmTask& t : st.tasks) {
+      for (size_t j = 0; j < nt; j++) {
+        const MsmTask& t = st.tasks[j];
         uint32_t cnt = 0;
         for (uint32_t k = 0; k < t.term_cnt; k++) cnt += (idx[t.term_off + k] & 0x7fffffffu) < fixed_.nbase;
         if (cnt < kFixedMinTerms) continue;
         for (uint32_t k = 0; k < t.term_cnt; k++)
           if ((idx[t.term_off + k] & 0x7fffffffu) < fixed_.nbase) idx[t.term_off + k] |= cdl::kMsmIdxFixed;
+        fixed_tasks.push_back((uint32_t)j);
       }
     }
   }
@@ -335,6 +338,14 @@ int32_t Engine::run_msm(MsmStage& st, const std::function<int32_t(cdl::Fr* d_sca
       if (cudaMalloc(&d_win_, wb + wb / 4) != cudaSuccess) return ctx_->fail(CDL_ERR_CUDA, "MSM scratch allocation failed");
       win_cap_ = wb + wb / 4;
     }
+    std::vector<uint32_t> fsubs;  // the chunks of those tasks
+    for (uint32_t j : fixed_tasks)
+      for (uint32_t c = 0; c < tasks2[j].sub_cnt; c++) fsubs.push_back(tasks2[j].sub_off + c);
+    if (!fsubs.empty()) {
+      if ((rc = reserve(s_fsub_, fsubs.size() * 4))) return rc;
+      memcpy(s_fsub_.h, fsubs.data(), fsubs.size() * 4);
+      CDL_CUDA(ctx_, cudaMemcpyAsync(s_fsub_.d, s_fsub_.h, fsubs.size() * 4, cudaMemcpyHostToDevice, ctx_->stream));
+    }
     memcpy(s_sub_.h, subs.data(), subs.size() * sizeof(cdl::MsmSub));
     memcpy(s_t2_.h, tasks2.data(), tasks2.size() * sizeof(cdl::MsmTask2));
     CDL_CUDA(ctx_, cudaMemcpyAsync(s_sub_.d, s_sub_.h, subs.size() * sizeof(cdl::MsmSub), cudaMemcpyHostToDevice, ctx_->stream));
@@ -342,7 +353,7 @@ int32_t Engine::run_msm(MsmStage& st, const std::function<int32_t(cdl::Fr* d_sca
     tick();
     cdl::launch_msm_tp(d_pool_, (const uint32_t*)s_idx_.d, (const cdl::Fr*)s_sc_.d, (int)nterm, (const cdl::MsmSub*)s_sub_.d,
                        (int)subs.size(), (const cdl::MsmTask2*)s_t2_.d, (int)nt, d_pool_, (uint8_t*)s_out_.d, d_win_,
-                       ctx_->stream, fixed_);
+                       ctx_->stream, fixed_, fsubs.empty() ? nullptr : (const uint32_t*)s_fsub_.d, (int)fsubs.size());
     tock(0, alg, 128.0 * nterm);
     launches += 3;
   } else {

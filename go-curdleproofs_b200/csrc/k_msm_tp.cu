@@ -228,12 +228,12 @@ static size_t bucket_scratch_bytes(int sms) { return (size_t)sms * kCtasPerSm * 
 // pass) is 22 table look-ups and mixed additions, no doublings, no buckets.  The lanes' sums are added
 // up with a shuffle tree into row 32 of the chunk's window sums, which k_msm_chunk_sum and
 // k_msm_combine_* carry along with weight 1.
-__global__ void __launch_bounds__(128)
+// One warp per CTA, launched for the listed chunks only (row 32 of every other chunk is zeroed = infinity).
+__global__ void __launch_bounds__(32)
 k_msm_fixed(const MsmRec* __restrict__ rec, const Fr* __restrict__ scalars, const MsmSub* __restrict__ subs, int nsub,
-            FixedTable ft, G1Jac* __restrict__ win) {
-  const int sub = blockIdx.x * 4 + (threadIdx.x >> 5);
-  if (sub >= nsub) return;  // the whole warp
-  const int lane = threadIdx.x & 31;
+            const uint32_t* __restrict__ fsubs, FixedTable ft, G1Jac* __restrict__ win) {
+  const int sub = (int)fsubs[blockIdx.x];  // the host lists the chunks of the tasks it flagged
+  const int lane = threadIdx.x;
   const MsmSub s = subs[sub];
   G1Xyzz acc;
   xyzz_set_inf(acc);
@@ -393,7 +393,7 @@ uint32_t msm_tp_pick_chunk(size_t nterm, int sm_count) {
 
 void launch_msm_tp(const G1Affine* points, const uint32_t* idx, const Fr* scalars, int nterm, const MsmSub* subs,
                    int nsub, const MsmTask2* tasks, int ntasks, G1Affine* out_aff, uint8_t* out_c48, void* scratch,
-                   cudaStream_t st, FixedTable ft) {
+                   cudaStream_t st, FixedTable ft, const uint32_t* fixed_subs, int nfixed_subs) {
   int dev = 0;
   cudaGetDevice(&dev);
   L2Persist g;
@@ -409,10 +409,13 @@ void launch_msm_tp(const G1Affine* points, const uint32_t* idx, const Fr* scalar
   G1Jac* win = (G1Jac*)((uint8_t*)rec + rec_bytes);
   G1Jac* wsum = (G1Jac*)((uint8_t*)win + win_bytes);
   uint4* buckets = (uint4*)((uint8_t*)wsum + ws_bytes);
-  const bool fixed = ft.tab != nullptr && ft.nbase > 0;
+  const bool fixed = ft.tab != nullptr && ft.nbase > 0 && fixed_subs != nullptr && nfixed_subs > 0;
   if (nterm > 0)
     k_msm_recode<<<(nterm + 127) / 128, 128, 0, st>>>(points, idx, scalars, rec, nterm, fixed ? ft.nbase : 0u);
-  if (fixed && nsub > 0) k_msm_fixed<<<(nsub + 3) / 4, 128, 0, st>>>(rec, scalars, subs, nsub, ft, win);
+  if (fixed) {
+    cudaMemsetAsync(win + (size_t)kTpWindows * nsub, 0, (size_t)nsub * sizeof(G1Jac), st);  // Z = 0: infinity
+    k_msm_fixed<<<nfixed_subs, 32, 0, st>>>(rec, scalars, subs, nsub, fixed_subs, ft, win);
+  }
   const int nrows = fixed ? kTpRows : kTpWindows;
   if (nsub > 0) {
     cudaMemsetAsync(next, 0, 4, st);

@@ -73,11 +73,13 @@ constexpr uint32_t kMsmChunk = 128;  // terms per bucket warp (msm_tp_pick_chunk
 size_t msm_tp_scratch_bytes(size_t nterm, size_t nsub, size_t ntasks);
 uint32_t msm_tp_pick_chunk(size_t nterm, int sm_count);
 void msm_l2_carveout(bool on);  // persisting-L2 window of the bucket scratch: held by the batched path only
-// ft: terms on the pool's first ft.nbase points are summed from the fixed-base tables by one warp per task
-// (k_msm_fixed) and skipped by the bucket warps
+// ft + fixed_subs: terms flagged kMsmIdxFixed (on the pool's first ft.nbase points) are summed from the fixed-base
+// tables by one warp per listed chunk (k_msm_fixed; fixed_subs = device list of the chunks holding such terms)
+// and skipped by the bucket warps
 void launch_msm_tp(const G1Affine* points, const uint32_t* idx, const Fr* scalars, int nterm, const MsmSub* subs,
                    int nsub, const MsmTask2* tasks, int ntasks, G1Affine* out_aff, uint8_t* out_c48, void* scratch,
-                   cudaStream_t st, FixedTable ft = FixedTable());
+                   cudaStream_t st, FixedTable ft = FixedTable(), const uint32_t* fixed_subs = nullptr,
+                   int nfixed_subs = 0);
 // host helper: cut tasks into subs
 template <class VecSub, class VecTask2>
 inline void msm_build_subs(const MsmTask* tasks, size_t ntasks, uint32_t chunk, VecSub& subs, VecTask2& tasks2) {
