@@ -108,6 +108,7 @@ def load_library():
     lib.cdl_g1_msm_device.argtypes = [vp, vp, vp, sz, C.c_uint32, C.c_uint32, i32, vp, f32p]
     lib.cdl_set_msm_window.argtypes = [vp, i32]
     lib.cdl_set_msm_batch_affine.argtypes = [vp, i32]
+    lib.cdl_set_fixed_base_min_batch.argtypes = [vp, i32]
     lib.cdl_comm_unique_id.argtypes = [vp]
     lib.cdl_comm_init.argtypes = [vp, vp, i32, i32]
     lib.cdl_comm_destroy.argtypes = [vp]
@@ -320,6 +321,10 @@ def _ctx_g1_msm_device(self, d_points, d_scalars, n: int, part_index: int = 0, p
 
 def _ctx_set_msm_window(self, bits: int):
     self._chk(self.lib.cdl_set_msm_window(self.h, bits))
+
+
+def _ctx_set_fixed_base_min_batch(self, instances: int):
+    self._chk(self.lib.cdl_set_fixed_base_min_batch(self.h, instances))
 
 
 def _ctx_set_msm_batch_affine(self, rounds: int):
@@ -562,6 +567,7 @@ Context.g1_msm_batch_device = _ctx_g1_msm_batch_device
 Context.g1_msm_device = _ctx_g1_msm_device
 Context.set_msm_window = _ctx_set_msm_window
 Context.set_msm_batch_affine = _ctx_set_msm_batch_affine
+Context.set_fixed_base_min_batch = _ctx_set_fixed_base_min_batch
 Context.comm_init = _ctx_comm_init
 Context.comm_destroy = _ctx_comm_destroy
 Context.g1_msm_sharded_device = _ctx_g1_msm_sharded_device

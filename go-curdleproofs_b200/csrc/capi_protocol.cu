@@ -321,6 +321,13 @@ int32_t cdl_crs_export(cdl_ctx* c, const cdl_crs* crs, cdl_g1_affine* points) {
 
 size_t cdl_crs_ell(const cdl_crs* crs) { return crs ? crs->ell : 0; }
 
+int32_t cdl_set_fixed_base_min_batch(cdl_ctx* c, int32_t instances) {
+  if (!c || instances < -1) return CDL_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(c->mu);
+  c->root()->fixed_min_batch = instances;
+  return CDL_OK;
+}
+
 void cdl_crs_free(cdl_crs* crs) {
   if (!crs) return;
   if (crs->d_points) { cudaSetDevice(crs->ctx->device); cudaFree(crs->d_points); }

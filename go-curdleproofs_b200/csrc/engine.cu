@@ -146,7 +146,9 @@ void Engine::select_fixed(const Layout& L, const cdl_crs* crs, size_t B) {
     const char* e = getenv("CDL_FIXED_BASE_MINB");
     return e ? atol(e) : 64L;
   }();
-  if (min_b <= 0 || (long)B < min_b) return;
+  const long over = ctx_->root()->fixed_min_batch;
+  const long lim = over >= 0 ? over : min_b;
+  if (lim <= 0 || (long)B < lim) return;
   std::lock_guard<std::mutex> lk(crs->fixed_mu);
   if (!crs->d_fixed && !crs->fixed_failed) {
     cdl::G1Affine* tab = nullptr;

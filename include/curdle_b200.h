@@ -140,6 +140,12 @@ int32_t cdl_crs_from_points(cdl_ctx* ctx, size_t ell, const cdl_g1_affine* point
 /* Same order as cdl_crs_from_points, ell + 9 points. */
 int32_t cdl_crs_export(cdl_ctx* ctx, const cdl_crs* crs, cdl_g1_affine* points);
 size_t cdl_crs_ell(const cdl_crs* crs);
+/* Fixed-base tables for the CRS points: protocol calls of at least `instances` proofs (per lane of a
+ * batched call) sum their multiples of Gs, Hs, H, Gt, Gu, Gsum, Hsum from tables of d * 2^(12 w) * P
+ * (4.3 MB per point, built on the device the first time a CRS is used that way and owned by the CRS
+ * object) instead of running buckets / double-and-add over them.  -1 = default (environment
+ * CDL_FIXED_BASE_MINB, else 64), 0 = never.  Tuning aid; results do not depend on it. */
+int32_t cdl_set_fixed_base_min_batch(cdl_ctx* ctx, int32_t instances);
 void cdl_crs_free(cdl_crs* crs);
 
 /* common.ShufflePermuteCommit (common/util.go:45-88): Ts = perm(k*Rs), Us = perm(k*Ss),

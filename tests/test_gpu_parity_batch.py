@@ -139,6 +139,28 @@ def test_whisk_n128_batch64_five_mutation_kinds_match_oracle(ctx, pkg):
     run_batch(ctx, pkg, 124, 64, 4576, 4, 2)
 
 
+def test_fixed_base_tables_give_the_same_bytes_and_verdicts(ctx, pkg):
+    """CRS fixed-base tables (cdl_set_fixed_base_min_batch; csrc/fixed_base.cuh) forced on for every call —
+    table look-ups for the commitments, B_c / B_a, the first round of both folding arguments, Gs' and the
+    verifier's merged CRS terms — against the oracle's proofs and verdicts with all five mutation kinds, at
+    n = 128 and (small, so that short windows, tiny tasks and the Gt / Gu slots of the first fold are hit) n = 16;
+    then the same batch with the tables off: identical bytes."""
+    try:
+        ctx.set_fixed_base_min_batch(1)
+        run_batch(ctx, pkg, 124, 64, 4576, 4, 2)
+        run_batch(ctx, pkg, 12, 20, 4576, 2, 3)
+        ell, B = 124, 40
+        crs = ctx.generate_crs(ell, pkg.Rand(0))
+        pre = b"".join(make_trackers(ctx, pkg, ell, 1000 + i % 3) for i in range(B))
+        on = ctx.whisk_generate_shuffle_proof_batch(crs, pre, [pkg.Rand(3000 + i) for i in range(B)])
+        ctx.set_fixed_base_min_batch(0)
+        off = ctx.whisk_generate_shuffle_proof_batch(crs, pre, [pkg.Rand(3000 + i) for i in range(B)])
+        assert bytes(on[0]) == bytes(off[0]) and bytes(on[1]) == bytes(off[1]) and on[2] == off[2] == [0] * B
+        crs.close()
+    finally:
+        ctx.set_fixed_base_min_batch(-1)
+
+
 def test_n256_batch_five_mutation_kinds_match_oracle(ctx, pkg):
     run_batch(ctx, pkg, 252, 20, 5056, 2, 1)
 
