@@ -14,6 +14,7 @@ hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
 hdr, data = rows[hi], rows[hi + 1:]
 CLASS = {"k_msm_recode": "msm_small", "k_msm_warp": "msm_small", "k_msm_warp_gmem": "msm_small", "k_msm_chunk_sum": "msm_small",
          "k_msm_combine_tp": "msm_small", "k_msm_combine_quad": "msm_small", "k_msm_small": "msm_small",
+         "k_msm_fixed": "msm_small",
          "k_elem_ops": "elem_scalar_mul", "k_elem_ops_quad": "elem_scalar_mul",
          "k_decompress_idx": "decompress", "k_compress_idx": "compress", "k_jac_to_affine": "compress"}
 STAGE_END = {"msm_small": ("k_msm_combine_tp", "k_msm_combine_quad", "k_msm_small"),
