@@ -1,6 +1,7 @@
 """__graft_entry__.smoke(): one small invocation of the hot path on cuda:0 — an MSM, a base fold and
-a Whisk shuffle-proof round trip (ell = 4) — checked against the CPU oracle and the committed golden
-fixture (the oracle is the checker only)."""
+a Whisk shuffle-proof round trip (ell = 4), a Pippenger MSM with and without batch-affine buckets, a batch of
+proofs through the throughput kernels with and without the CRS fixed-base tables — checked against the CPU
+oracle and the committed golden fixture (the oracle is the checker only)."""
 import importlib
 import json
 import os
@@ -46,5 +47,27 @@ def run():
     big = ctx.g1_scalar_mul_affine(aff_enc(b.G1_GEN) * n, frs_enc(a), broadcast=False)
     want = b.g1_mul(b.G1_GEN, sum(u * v for u, v in zip(a, s)) % b.R)
     assert jac_dec(ctx.g1_msm(big, frs_enc(s))) == want, "large MSM mismatch vs oracle"
+    # the same MSM with batch-affine bucket accumulation forced (narrow windows, three pair-sum rounds)
+    ctx.set_msm_window(7)
+    ctx.set_msm_batch_affine(3)
+    try:
+        assert jac_dec(ctx.g1_msm(big, frs_enc(s))) == want, "batch-affine MSM mismatch vs oracle"
+    finally:
+        ctx.set_msm_window(0)
+        ctx.set_msm_batch_affine(-1)
+    # a batch of Whisk proofs through the throughput kernels, with and without the CRS fixed-base tables:
+    # both runs give the same bytes, every proof validates
+    B = 128
+    outs = []
+    for min_b in (1, 0):
+        ctx.set_fixed_base_min_batch(min_b)
+        rb = [pkg.Rand(200 + i) for i in range(B)]
+        outs.append(ctx.whisk_generate_shuffle_proof_batch(crs, pre * B, rb))
+    ctx.set_fixed_base_min_batch(1)
+    assert bytes(outs[0][0]) == bytes(outs[1][0]) and bytes(outs[0][1]) == bytes(outs[1][1]), "fixed-base tables changed bytes"
+    assert outs[0][2] == [0] * B
+    ok, st = ctx.whisk_is_valid_shuffle_proof_batch(crs, pre * B, outs[0][0], outs[0][1], [pkg.Rand(300 + i) for i in range(B)])
+    ctx.set_fixed_base_min_batch(-1)
+    assert ok == [1] * B and st == [0] * B, "batched validation failed"
     print("smoke ok:", ctx.device_info())
     ctx.close()
