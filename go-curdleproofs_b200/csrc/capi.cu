@@ -192,6 +192,9 @@ int32_t cdl_g1_msm_batch_device(cdl_ctx* c, cdl_g1_affine* d_pool, const uint32_
     tasks[j].pad = 0;
     if (tasks[j].term_cnt > max_terms) max_terms = tasks[j].term_cnt;
   }
+  // pool indices are 30 bits: bit 31 negates, bit 30 is the kernels' own flag
+  for (size_t t = 0; t < total; t++)
+    if (idx[t] & 0x40000000u) return c->fail(CDL_ERR_INVALID_ARG, "msm_batch_device: pool index of term %zu exceeds 2^30 - 1", t);
   Fr* d_sc = (Fr*)c->buf(1, (total + 1) * sizeof(Fr));
   uint32_t* d_idx = (uint32_t*)c->buf(2, (total + 1) * sizeof(uint32_t));
   MsmTask* d_tasks = (MsmTask*)c->buf(3, k * sizeof(MsmTask));

@@ -255,7 +255,7 @@ int32_t cdl_g1_scalar_mul_affine_device(cdl_ctx* ctx, const cdl_g1_affine* d_in,
 int32_t cdl_g1_fold_device(cdl_ctx* ctx, cdl_g1_affine* d_L, const cdl_g1_affine* d_R, const cdl_fr* d_x, size_t n);
 
 /* (*G1Jac).MultiExp for k independent MSMs whose BASES STAY ON THE DEVICE: term t of MSM j is
- * scalars[t] * d_pool[idx[t]] (bit 31 of idx[t] negates the base), t in [offsets[j], offsets[j+1]).
+ * scalars[t] * d_pool[idx[t]] (bit 31 of idx[t] negates the base; pool indices are below 2^30), t in [offsets[j], offsets[j+1]).
  * idx / scalars / offsets / out_slot are HOST arrays - what the Go orchestration computes between
  * rounds - while d_pool is a device array of affine points (cdl_dev_alloc + cdl_dev_upload, folded in
  * place with cdl_g1_fold_device), so the folded base vectors of innerproductargument.go:100-172 and
