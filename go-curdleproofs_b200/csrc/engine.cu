@@ -614,6 +614,7 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
 
   // ---- grand-product argument (grandproductargument.go:52-92)
   std::vector<Fr> gp_alpha(B), gp_beta(B), gp_beta_inv(B);
+  std::vector<std::vector<Fr>> gp_scale;  // G'[i] = gp_scale[b][i] * (Gs || Hs)[i]
   par(B, [&](size_t b) {
     ProveState& s = *S[b];
     s.tr.append_points("gprod_step1", s.Bp, 1);
@@ -640,9 +641,16 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
   std::vector<std::vector<Fr>> r_b_plus_alpha(B);
   std::vector<Fr> beta_l1(B);
   {
-    // Gs'[i] = beta^-(i+1) Gs[i], Hs'[i] = beta^-(ell+1) Hs[i]  (:94-103) -> Gp; G = Gs || Hs
-    std::vector<ElemOp> ops((size_t)B * n);
+    // Gs'[i] = beta^-(i+1) Gs[i], Hs'[i] = beta^-(ell+1) Hs[i]  (:94-103) -> Gp; G = Gs || Hs.
+    // Only the LOWER half of G' = Gs' || Hs' is ever materialised: everything the prover does with the upper
+    // half before the first fold is linear in it — B_d, the self-check, L_D / R_D of the first round and the
+    // first fold G'_L + gamma^-1 G'_R — and is taken on the CRS points themselves with the scale factor
+    // gp_scale[i] = beta^-(i+1) (beta^-(ell+1) for the Hs part) multiplied into the scalar, where the
+    // fixed-base tables (fixed_base.cuh) apply.
+    const uint32_t nh = n / 2;
+    std::vector<ElemOp> ops((size_t)B * nh);
     std::vector<Fr> sc((size_t)B * (ell + 1));
+    gp_scale.assign(B, std::vector<Fr>());
     par(B, [&](size_t b) {
       ProveState& s = *S[b];
       r_b_plus_alpha[b].resize(kBlinders);
@@ -657,14 +665,20 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
       uint32_t base = L.base((uint32_t)b);
       Fr t = beta_inv;
       Fr* scb = sc.data() + b * (ell + 1);
+      std::vector<Fr>& scale = gp_scale[b];
+      scale.resize(n);
       for (uint32_t i = 0; i < ell; i++) {
         scb[i] = t;
-        ops[b * n + i] = ElemOp{L.Gs + i, cdl::kNoPoint, base + L.Gp + i, (uint32_t)(b * (ell + 1) + i)};
+        scale[i] = t;
+        if (i < nh) ops[b * nh + i] = ElemOp{L.Gs + i, cdl::kNoPoint, base + L.Gp + i, (uint32_t)(b * (ell + 1) + i)};
         t = fr_mul(t, beta_inv);
       }
       scb[ell] = t;
-      for (uint32_t j = 0; j < kBlinders; j++)
-        ops[b * n + ell + j] = ElemOp{L.Hs + j, cdl::kNoPoint, base + L.Gp + ell + j, (uint32_t)(b * (ell + 1) + ell)};
+      for (uint32_t j = 0; j < kBlinders; j++) {
+        scale[ell + j] = t;
+        if (ell + j < nh)  // only for ell < 4
+          ops[b * nh + ell + j] = ElemOp{L.Hs + j, cdl::kNoPoint, base + L.Gp + ell + j, (uint32_t)(b * (ell + 1) + ell)};
+      }
     });
     if ((rc = run_elem(ops, sc))) return rc;
     std::vector<cdl::CopyRange> cr(B);
@@ -717,13 +731,13 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
       sl.end();
       sl.begin(base + L.scratch + 3);  // msm(G', d) must equal D
       if (!witness_is_ours)
-        for (uint32_t i = 0; i < n; i++) sl.term(base + L.Gp + i, s.ds[i]);
+        for (uint32_t i = 0; i < n; i++) sl.term(L.Gs + i, fr_mul(s.ds[i], gp_scale[b][i]));  // G'[i] = scale[i] * (Gs || Hs)[i]
       sl.end();
       sl.begin(base + L.scratch + 4);  // B_c: G is still the unfolded Gs || Hs, named by its CRS-image indices
       for (uint32_t i = 0; i < n; i++) sl.term(L.Gs + i, rs_c[b][i]);  // (fixed-base tables, fixed_base.cuh)
       sl.end();
       sl.begin(base + L.scratch + 5);  // B_d
-      for (uint32_t i = 0; i < n; i++) sl.term(base + L.Gp + i, rs_d[b][i]);
+      for (uint32_t i = 0; i < n; i++) sl.term(L.Gs + i, fr_mul(rs_d[b][i], gp_scale[b][i]));
       sl.end();
     });
     if ((rc = run_msm(st))) return rc;
@@ -765,19 +779,29 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
       sl.term(L.H, fr_mul(s.beta_ipa, fr_inner(c_L, d_R, half)));
       sl.end();
       sl.begin(base + L.scratch + 1);  // L_D = <d_R, G'_L>
-      for (uint32_t i = 0; i < half; i++) sl.term(base + L.Gp + i, d_R[i]);
+      const bool first_round = half == n / 2;  // G' unfolded: scale[i] * (Gs || Hs)[i], see the Gs' stage
+      for (uint32_t i = 0; i < half; i++) {
+        if (first_round) sl.term(L.Gs + i, fr_mul(d_R[i], gp_scale[b][i]));
+        else sl.term(base + L.Gp + i, d_R[i]);
+      }
       sl.end();
       sl.begin(base + L.scratch + 2);  // R_C = <c_R, G_L> + <c_R, d_L> * (beta*H)
       for (uint32_t i = 0; i < half; i++) sl.term(g0 + i, c_R[i]);
       sl.term(L.H, fr_mul(s.beta_ipa, fr_inner(c_R, d_L, half)));
       sl.end();
       sl.begin(base + L.scratch + 3);  // R_D = <d_L, G'_R>
-      for (uint32_t i = 0; i < half; i++) sl.term(base + L.Gp + half + i, d_L[i]);
+      for (uint32_t i = 0; i < half; i++) {
+        if (first_round) sl.term(L.Gs + half + i, fr_mul(d_L[i], gp_scale[b][half + i]));
+        else sl.term(base + L.Gp + half + i, d_L[i]);
+      }
       sl.end();
     });
     if ((rc = run_msm(st))) return rc;
     std::vector<ElemOp> ops(half > 1 ? (size_t)B * 2 * (half) : 0);
-    std::vector<Fr> sc((size_t)B * 2);
+    const bool first_fold = half == n / 2;
+    // first fold of G': the right half is not materialised (see the Gs' stage); its source is the CRS point
+    // with the per-element scalar gamma^-1 * scale[half + i]
+    std::vector<Fr> sc((size_t)B * 2 + (first_fold && half > 1 ? (size_t)B * half : 0));
     par(B, [&](size_t b) {
       ProveState& s = *S[b];
       const uint8_t *lc = sb.out((uint32_t)b, 0), *ld = sb.out((uint32_t)b, 1), *rcc = sb.out((uint32_t)b, 2), *rd = sb.out((uint32_t)b, 3);
@@ -804,7 +828,13 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
         const uint32_t g0 = half == n / 2 ? L.Gs : base + L.G;  // first fold: sources are the CRS points
         for (uint32_t i = 0; i < half; i++) {
           o[i] = ElemOp{g0 + half + i, g0 + i, base + L.G + i, (uint32_t)(2 * b)};
-          o[half + i] = ElemOp{base + L.Gp + half + i, base + L.Gp + i, base + L.Gp + i, (uint32_t)(2 * b + 1)};
+          if (first_fold) {
+            const uint32_t si = (uint32_t)(2 * B + b * half + i);
+            sc[si] = fr_mul(gamma_inv, gp_scale[b][half + i]);
+            o[half + i] = ElemOp{L.Gs + half + i, base + L.Gp + i, base + L.Gp + i, si};
+          } else {
+            o[half + i] = ElemOp{base + L.Gp + half + i, base + L.Gp + i, base + L.Gp + i, (uint32_t)(2 * b + 1)};
+          }
         }
       }
     });
