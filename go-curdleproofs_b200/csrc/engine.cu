@@ -615,6 +615,16 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
   // ---- grand-product argument (grandproductargument.go:52-92)
   std::vector<Fr> gp_alpha(B), gp_beta(B), gp_beta_inv(B);
   std::vector<std::vector<Fr>> gp_scale;  // G'[i] = gp_scale[b][i] * (Gs || Hs)[i]
+  // With the CRS fixed-base tables at hand (fixed_base.cuh) the CRS-based vectors of the two folding arguments —
+  // G and G' of the inner-product argument, Gm of the same-multiscalar argument — are not folded in their first
+  // two rounds at all: a folded base is a short linear combination of CRS points,
+  //   V1[i] = V[i] + x1 V[i + n/2],   V2[i] = V[i] + x1 V[i + n/2] + x2 V[i + n/4] + x1 x2 V[i + 3n/4],
+  // so the second round's MSMs take two CRS terms per base (220 products each, against 700 for a bucket term
+  // plus 1 500 for the scalar multiplication that would have produced the base) and V2 is built once, straight
+  // from the CRS, by three or four chained table multiplications per element.  Rounds three onwards fold as
+  // before.  Small batches (no tables) keep the plain schedule: it has fewer launches.
+  const bool lazy = fixed_.tab != nullptr && n >= 8;
+  std::vector<std::array<Fr, 4>> ipa_x(B), sm_x(B);  // gamma_0, gamma_0^-1, gamma_1, gamma_1^-1 of the two arguments
   par(B, [&](size_t b) {
     ProveState& s = *S[b];
     s.tr.append_points("gprod_step1", s.Bp, 1);
@@ -647,7 +657,7 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
     // first fold G'_L + gamma^-1 G'_R — and is taken on the CRS points themselves with the scale factor
     // gp_scale[i] = beta^-(i+1) (beta^-(ell+1) for the Hs part) multiplied into the scalar, where the
     // fixed-base tables (fixed_base.cuh) apply.
-    const uint32_t nh = n / 2;
+    const uint32_t nh = lazy ? 0 : n / 2;  // lazy: G' is first materialised after the second round, from the CRS
     std::vector<ElemOp> ops((size_t)B * nh);
     std::vector<Fr> sc((size_t)B * (ell + 1));
     gp_scale.assign(B, std::vector<Fr>());
@@ -764,44 +774,56 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
       s.ds[i] = fr_add(rs_d[b][i], fr_mul(alpha, s.ds[i]));
     }
   });
-  for (uint32_t half = n / 2; half >= 1; half /= 2) {
-    StageBuilder sb(st, B, 4 * half + 2, 4);
+  uint32_t ipa_round = 0;
+  for (uint32_t half = n / 2; half >= 1; half /= 2, ipa_round++) {
+    const uint32_t round = ipa_round;
+    const bool expand = lazy && round == 1;  // bases of this round are pairs of CRS points
+    StageBuilder sb(st, B, (expand ? 8 : 4) * half + 2, 4);
     par(B, [&](size_t b) {
       ProveState& s = *S[b];
       uint32_t base = L.base((uint32_t)b);
       const Fr *c_L = s.cs.data(), *c_R = s.cs.data() + half, *d_L = s.ds.data(), *d_R = s.ds.data() + half;
       MsmSlice sl = sb.slice((uint32_t)b);
-      // first round: G is the unfolded Gs || Hs (adjacent in the CRS image); naming the CRS points themselves
-      // lets the launch use their fixed-base tables
-      const uint32_t g0 = half == n / 2 ? L.Gs : base + L.G;
+      const std::vector<Fr>& scale = gp_scale[b];
+      const uint32_t len1 = n / 2;
+      // term a * G[e] / a * G'[e] of the current (possibly virtual) vectors.  First round: G is the unfolded
+      // Gs || Hs (adjacent in the CRS image) and G'[e] = scale[e] * (Gs || Hs)[e]: naming the CRS points themselves
+      // lets the launch use their fixed-base tables.
+      auto g_term = [&](uint32_t e, const Fr& a) {
+        if (round == 0) sl.term(L.Gs + e, a);
+        else if (expand) { sl.term(L.Gs + e, a); sl.term(L.Gs + e + len1, fr_mul(a, ipa_x[b][0])); }
+        else sl.term(base + L.G + e, a);
+      };
+      auto gp_term = [&](uint32_t e, const Fr& a) {
+        if (round == 0) sl.term(L.Gs + e, fr_mul(a, scale[e]));
+        else if (expand) {
+          sl.term(L.Gs + e, fr_mul(a, scale[e]));
+          sl.term(L.Gs + e + len1, fr_mul(fr_mul(a, ipa_x[b][1]), scale[e + len1]));
+        } else sl.term(base + L.Gp + e, a);
+      };
       sl.begin(base + L.scratch);  // L_C = <c_L, G_R> + <c_L, d_R> * (beta*H)
-      for (uint32_t i = 0; i < half; i++) sl.term(g0 + half + i, c_L[i]);
+      for (uint32_t i = 0; i < half; i++) g_term(half + i, c_L[i]);
       sl.term(L.H, fr_mul(s.beta_ipa, fr_inner(c_L, d_R, half)));
       sl.end();
       sl.begin(base + L.scratch + 1);  // L_D = <d_R, G'_L>
-      const bool first_round = half == n / 2;  // G' unfolded: scale[i] * (Gs || Hs)[i], see the Gs' stage
-      for (uint32_t i = 0; i < half; i++) {
-        if (first_round) sl.term(L.Gs + i, fr_mul(d_R[i], gp_scale[b][i]));
-        else sl.term(base + L.Gp + i, d_R[i]);
-      }
+      for (uint32_t i = 0; i < half; i++) gp_term(i, d_R[i]);
       sl.end();
       sl.begin(base + L.scratch + 2);  // R_C = <c_R, G_L> + <c_R, d_L> * (beta*H)
-      for (uint32_t i = 0; i < half; i++) sl.term(g0 + i, c_R[i]);
+      for (uint32_t i = 0; i < half; i++) g_term(i, c_R[i]);
       sl.term(L.H, fr_mul(s.beta_ipa, fr_inner(c_R, d_L, half)));
       sl.end();
       sl.begin(base + L.scratch + 3);  // R_D = <d_L, G'_R>
-      for (uint32_t i = 0; i < half; i++) {
-        if (first_round) sl.term(L.Gs + half + i, fr_mul(d_L[i], gp_scale[b][half + i]));
-        else sl.term(base + L.Gp + half + i, d_L[i]);
-      }
+      for (uint32_t i = 0; i < half; i++) gp_term(half + i, d_L[i]);
       sl.end();
     });
     if ((rc = run_msm(st))) return rc;
-    std::vector<ElemOp> ops(half > 1 ? (size_t)B * 2 * (half) : 0);
-    const bool first_fold = half == n / 2;
-    // first fold of G': the right half is not materialised (see the Gs' stage); its source is the CRS point
-    // with the per-element scalar gamma^-1 * scale[half + i]
-    std::vector<Fr> sc((size_t)B * 2 + (first_fold && half > 1 ? (size_t)B * half : 0));
+    // folds after this round: none after the first when lazy; V2 from the CRS after the second (below)
+    const bool plain_fold = half > 1 && !(lazy && round <= 1);
+    const bool first_fold = round == 0;
+    std::vector<ElemOp> ops(plain_fold ? (size_t)B * 2 * (half) : 0);
+    // first fold of G' (plain schedule): the right half is not materialised (see the Gs' stage); its source is the
+    // CRS point with the per-element scalar gamma^-1 * scale[half + i]
+    std::vector<Fr> sc((size_t)B * 2 + (first_fold && plain_fold ? (size_t)B * half : 0));
     par(B, [&](size_t b) {
       ProveState& s = *S[b];
       const uint8_t *lc = sb.out((uint32_t)b, 0), *ld = sb.out((uint32_t)b, 1), *rcc = sb.out((uint32_t)b, 2), *rd = sb.out((uint32_t)b, 3);
@@ -822,10 +844,11 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
       }
       sc[2 * b] = gamma;
       sc[2 * b + 1] = gamma_inv;
-      if (half > 1) {  // the folded bases of the last round are never read again
+      if (round <= 1) { ipa_x[b][2 * round] = gamma; ipa_x[b][2 * round + 1] = gamma_inv; }
+      if (plain_fold) {  // the folded bases of the last round are never read again
         uint32_t base = L.base((uint32_t)b);
         ElemOp* o = ops.data() + b * 2 * half;
-        const uint32_t g0 = half == n / 2 ? L.Gs : base + L.G;  // first fold: sources are the CRS points
+        const uint32_t g0 = first_fold ? L.Gs : base + L.G;  // first fold: sources are the CRS points
         for (uint32_t i = 0; i < half; i++) {
           o[i] = ElemOp{g0 + half + i, g0 + i, base + L.G + i, (uint32_t)(2 * b)};
           if (first_fold) {
@@ -839,6 +862,40 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
       }
     });
     if ((rc = run_elem(ops, sc))) return rc;
+    if (lazy && round == 1 && half > 1) {
+      // G2[i] = C[i] + x1 C[i+2q] + x2 C[i+q] + x1 x2 C[i+3q] with x = gamma, C = Gs || Hs, q = half;
+      // G'2[i] = s[i] C[i] + y1 s[i+2q] C[i+2q] + y2 s[i+q] C[i+q] + y1 y2 s[i+3q] C[i+3q] with y = gamma^-1,
+      // s = gp_scale: four chained launches of table multiplications (the last one for G' only).
+      const uint32_t q = half;
+      for (int pass = 0; pass < 4; pass++) {
+        const uint32_t per = pass < 3 ? 2 * q : q;
+        std::vector<ElemOp> o2((size_t)B * per);
+        std::vector<Fr> s2((size_t)B * (q + 1));  // per proof: q per-element scalars for G', one shared scalar for G
+        par(B, [&](size_t b) {
+          const uint32_t base = L.base((uint32_t)b);
+          const std::vector<Fr>& scale = gp_scale[b];
+          const Fr x1 = ipa_x[b][0], y1 = ipa_x[b][1], x2 = ipa_x[b][2], y2 = ipa_x[b][3];
+          ElemOp* o = o2.data() + b * per;
+          Fr* sv = s2.data() + b * (q + 1);
+          const uint32_t sbase = (uint32_t)(b * (q + 1));
+          // offsets of the CRS point each pass adds, for G (first pass: add C[i] as the plain summand) and G'
+          static const uint32_t g_off[3] = {2, 1, 3}, gp_off[4] = {0, 2, 1, 3};
+          if (pass < 3) {
+            sv[q] = pass == 0 ? x1 : pass == 1 ? x2 : fr_mul(x1, x2);
+            for (uint32_t i = 0; i < q; i++)
+              o[i] = ElemOp{L.Gs + i + g_off[pass] * q, pass == 0 ? L.Gs + i : base + L.G + i, base + L.G + i, sbase + q};
+          }
+          const Fr yc = pass == 0 ? FR_ONE : pass == 1 ? y1 : pass == 2 ? y2 : fr_mul(y1, y2);
+          ElemOp* op = o + (pass < 3 ? q : 0);
+          for (uint32_t i = 0; i < q; i++) {
+            const uint32_t e = i + gp_off[pass] * q;
+            sv[i] = pass == 0 ? scale[e] : fr_mul(yc, scale[e]);
+            op[i] = ElemOp{L.Gs + e, pass == 0 ? cdl::kNoPoint : base + L.Gp + i, base + L.Gp + i, sbase + i};
+          }
+        });
+        if ((rc = run_elem(o2, s2))) return rc;
+      }
+    }
   }
   for (uint32_t b = 0; b < B; b++) { S[b]->c0 = S[b]->cs[0]; S[b]->d0 = S[b]->ds[0]; }
 
@@ -978,33 +1035,42 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
     });
   }
   // ---- same-multiscalar rounds (samemultiscalarargument.go:85-140)
-  for (uint32_t half = n / 2; half >= 1; half /= 2) {
-    StageBuilder sb(st, B, 6 * half, 6);
+  // Gm = Gs || Hs[0..2) || Gt || Gu in CRS-image indices
+  auto cm = [&](uint32_t i) { return i < ell + 2 ? L.Gs + i : L.Gt + (i - ell - 2); };
+  uint32_t sm_round = 0;
+  for (uint32_t half = n / 2; half >= 1; half /= 2, sm_round++) {
+    const uint32_t round = sm_round;
+    const bool expand = lazy && round == 1;  // Gm's bases of this round are pairs of CRS points (see `lazy`)
+    StageBuilder sb(st, B, (expand ? 8 : 6) * half, 6);
     par(B, [&](size_t b) {
       ProveState& s = *S[b];
       uint32_t base = L.base((uint32_t)b);
       const Fr *x_L = s.x.data(), *x_R = s.x.data() + half;
       MsmSlice sl = sb.slice((uint32_t)b);
       const uint32_t vec[3] = {L.Gm, L.Tp, L.Up};
+      const uint32_t len1 = n / 2;
       // first round: Gm is still Gs || Hs[0..2) || Gt || Gu, named by its CRS-image indices (fixed-base tables)
-      const bool first = half == n / 2;
-      auto pt = [&](int v, uint32_t i) {
-        if (v == 0 && first) return i < ell + 2 ? L.Gs + i : L.Gt + (i - ell - 2);
-        return base + vec[v] + i;
+      auto term = [&](int v, uint32_t e, const Fr& a) {
+        if (v == 0 && round == 0) sl.term(cm(e), a);
+        else if (v == 0 && expand) { sl.term(cm(e), a); sl.term(cm(e + len1), fr_mul(a, sm_x[b][0])); }
+        else sl.term(base + vec[v] + e, a);
       };
       for (int v = 0; v < 3; v++) {  // L_A, L_T, L_U over the right halves with x_L
         sl.begin(base + L.scratch + v);
-        for (uint32_t i = 0; i < half; i++) sl.term(pt(v, half + i), x_L[i]);
+        for (uint32_t i = 0; i < half; i++) term(v, half + i, x_L[i]);
         sl.end();
       }
       for (int v = 0; v < 3; v++) {  // R_A, R_T, R_U over the left halves with x_R
         sl.begin(base + L.scratch + 3 + v);
-        for (uint32_t i = 0; i < half; i++) sl.term(pt(v, i), x_R[i]);
+        for (uint32_t i = 0; i < half; i++) term(v, i, x_R[i]);
         sl.end();
       }
     });
     if ((rc = run_msm(st))) return rc;
-    std::vector<ElemOp> ops(half > 1 ? (size_t)B * 3 * half : 0);
+    // T' and U' fold every round; Gm as well, except in the first two rounds of the lazy schedule
+    const bool fold_gm = !(lazy && round <= 1);
+    const uint32_t nvec = fold_gm ? 3 : 2;
+    std::vector<ElemOp> ops(half > 1 ? (size_t)B * nvec * half : 0);
     std::vector<Fr> sc(B);
     par(B, [&](size_t b) {
       ProveState& s = *S[b];
@@ -1019,23 +1085,41 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
       Fr gamma_inv = fr_inv(gamma);
       for (uint32_t i = 0; i < half; i++) s.x[i] = fr_add(s.x[i], fr_mul(gamma_inv, s.x[half + i]));
       sc[b] = gamma;
+      if (round <= 1) { sm_x[b][2 * round] = gamma; sm_x[b][2 * round + 1] = gamma_inv; }
       if (half > 1) {
         uint32_t base = L.base((uint32_t)b);
         const uint32_t vec[3] = {L.Tp, L.Up, L.Gm};
-        const bool first = half == n / 2;  // first fold of Gm: sources are the CRS points
-        ElemOp* o = ops.data() + b * 3 * half;
-        for (int v = 0; v < 3; v++)
+        const bool first = round == 0;  // first fold of Gm: sources are the CRS points
+        ElemOp* o = ops.data() + b * nvec * half;
+        for (uint32_t v = 0; v < nvec; v++)
           for (uint32_t i = 0; i < half; i++) {
             uint32_t src = base + vec[v] + half + i, add = base + vec[v] + i;
             if (v == 2 && first) {
-              src = half + i < ell + 2 ? L.Gs + half + i : L.Gt + (half + i - ell - 2);
-              add = L.Gs + i;  // i < half <= ell + 2
+              src = cm(half + i);
+              add = cm(i);
             }
             o[v * half + i] = ElemOp{src, add, base + vec[v] + i, (uint32_t)b};
           }
       }
     });
     if ((rc = run_elem(ops, sc))) return rc;
+    if (lazy && round == 1 && half > 1) {
+      // Gm2[i] = C[i] + x1 C[i+2q] + x2 C[i+q] + x1 x2 C[i+3q], x = gamma, C = Gm in CRS indices, q = half
+      const uint32_t q = half;
+      for (int pass = 0; pass < 3; pass++) {
+        std::vector<ElemOp> o2((size_t)B * q);
+        std::vector<Fr> s2(B);
+        par(B, [&](size_t b) {
+          const uint32_t base = L.base((uint32_t)b);
+          static const uint32_t off[3] = {2, 1, 3};
+          s2[b] = pass == 0 ? sm_x[b][0] : pass == 1 ? sm_x[b][2] : fr_mul(sm_x[b][0], sm_x[b][2]);
+          ElemOp* o = o2.data() + b * q;
+          for (uint32_t i = 0; i < q; i++)
+            o[i] = ElemOp{cm(i + off[pass] * q), pass == 0 ? cm(i) : base + L.Gm + i, base + L.Gm + i, (uint32_t)b};
+        });
+        if ((rc = run_elem(o2, s2))) return rc;
+      }
+    }
   }
 
   // ---- serialize (curdleproof.go:358-387 and the sub-proof Serialize methods)
