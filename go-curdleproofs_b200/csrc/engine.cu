@@ -323,7 +323,9 @@ int32_t Engine::run_msm(MsmStage& st, const std::function<int32_t(cdl::Fr* d_sca
     if (brc) return brc;
   }
   double alg = 0;
-  for (auto& t : st.tasks) alg += msm_algorithmic_modmul(t.term_cnt);
+  // credited per task at the reference's term count (a base expanded into several CRS terms counts once)
+  for (size_t j = 0; j < st.tasks.size(); j++)
+    alg += msm_algorithmic_modmul(st.tasks[j].term_cnt - (st.extra.size() == st.tasks.size() ? st.extra[j] : 0));
   if (throughput) {
     // throughput path: recode + warp-per-chunk + per-task combine
     std::vector<cdl::MsmSub> subs;
@@ -405,12 +407,14 @@ struct StageBuilder {
     st.idx.assign((size_t)B * terms, 0);
     st.sc.assign((size_t)B * terms, FR_ZERO);
     st.tasks.assign((size_t)B * tasks, MsmTask{0, 0, 0, 0});
+    st.extra.assign((size_t)B * tasks, 0);
   }
   MsmSlice slice(uint32_t b) {
     MsmSlice s;
     s.idx = st.idx.data() + (size_t)b * terms_per;
     s.sc = st.sc.data() + (size_t)b * terms_per;
     s.tasks = st.tasks.data() + (size_t)b * tasks_per;
+    s.extra = st.extra.data() + (size_t)b * tasks_per;
     s.term_base = b * terms_per;
     return s;
   }
@@ -791,14 +795,14 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
       // lets the launch use their fixed-base tables.
       auto g_term = [&](uint32_t e, const Fr& a) {
         if (round == 0) sl.term(L.Gs + e, a);
-        else if (expand) { sl.term(L.Gs + e, a); sl.term(L.Gs + e + len1, fr_mul(a, ipa_x[b][0])); }
+        else if (expand) { sl.term(L.Gs + e, a); sl.term_more(L.Gs + e + len1, fr_mul(a, ipa_x[b][0])); }
         else sl.term(base + L.G + e, a);
       };
       auto gp_term = [&](uint32_t e, const Fr& a) {
         if (round == 0) sl.term(L.Gs + e, fr_mul(a, scale[e]));
         else if (expand) {
           sl.term(L.Gs + e, fr_mul(a, scale[e]));
-          sl.term(L.Gs + e + len1, fr_mul(fr_mul(a, ipa_x[b][1]), scale[e + len1]));
+          sl.term_more(L.Gs + e + len1, fr_mul(fr_mul(a, ipa_x[b][1]), scale[e + len1]));
         } else sl.term(base + L.Gp + e, a);
       };
       sl.begin(base + L.scratch);  // L_C = <c_L, G_R> + <c_L, d_R> * (beta*H)
@@ -1052,7 +1056,7 @@ int32_t Engine::prove(const Layout& L, uint32_t B, const cdl_crs* crs, const std
       // first round: Gm is still Gs || Hs[0..2) || Gt || Gu, named by its CRS-image indices (fixed-base tables)
       auto term = [&](int v, uint32_t e, const Fr& a) {
         if (v == 0 && round == 0) sl.term(cm(e), a);
-        else if (v == 0 && expand) { sl.term(cm(e), a); sl.term(cm(e + len1), fr_mul(a, sm_x[b][0])); }
+        else if (v == 0 && expand) { sl.term(cm(e), a); sl.term_more(cm(e + len1), fr_mul(a, sm_x[b][0])); }
         else sl.term(base + vec[v] + e, a);
       };
       for (int v = 0; v < 3; v++) {  // L_A, L_T, L_U over the right halves with x_L

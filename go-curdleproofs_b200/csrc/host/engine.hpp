@@ -61,7 +61,10 @@ struct MsmStage {
   std::vector<Fr> sc;
   std::vector<cdl::MsmTask> tasks;
   std::vector<uint8_t> out48;  // filled by run: tasks.size() * 48
-  void clear() { idx.clear(); sc.clear(); tasks.clear(); }
+  // host-side accounting only (empty, or one entry per task): terms of the task that exist because one base of
+  // the reference's MSM was written as several CRS points (lazy folding); not counted as algorithmic work
+  std::vector<uint32_t> extra;
+  void clear() { idx.clear(); sc.clear(); tasks.clear(); extra.clear(); }
 };
 
 // per-instance builder writing into a pre-sized slice of a stage
@@ -69,6 +72,7 @@ struct MsmSlice {
   uint32_t* idx;
   Fr* sc;
   cdl::MsmTask* tasks;
+  uint32_t* extra = nullptr;  // MsmStage::extra of this slice's tasks
   uint32_t term_base;  // global index of idx[0]
   uint32_t nterm = 0, ntask = 0;
   void begin(uint32_t out_idx) {
@@ -82,6 +86,11 @@ struct MsmSlice {
     sc[nterm] = s;
     nterm++;
     tasks[ntask].term_cnt++;
+  }
+  // a further term of the base the previous term() call started (see MsmStage::extra)
+  void term_more(uint32_t point, const Fr& s) {
+    term(point, s);
+    if (extra) extra[ntask]++;
   }
   void end() { ntask++; }
 };
