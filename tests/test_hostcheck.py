@@ -20,7 +20,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 def hc(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("hc") / "libhostcheck.so")
     src = os.path.join(HERE, "hostcheck", "hostcheck.cpp")
-    subprocess.run(["g++", "-O2", "-std=c++17", "-x", "c++", "-shared", "-fPIC", "-o", out, src], check=True)
+    # CDL_HOSTCHECK_FLAGS="-fsanitize=undefined -fno-sanitize-recover=all -static-libubsan" runs the tier under UBSan
+    extra = os.environ.get("CDL_HOSTCHECK_FLAGS", "").split()
+    subprocess.run(["g++", "-O2", "-std=c++17", *extra, "-x", "c++", "-shared", "-fPIC", "-o", out, src], check=True)
     return ctypes.CDLL(out)
 
 
