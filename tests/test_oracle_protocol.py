@@ -100,3 +100,41 @@ def test_msm_accumulator():  # msmaccumulator_test.go:12-50
     xs = rand.get_frs(2)
     acc.accumulate_check(bls.g1_msm(pts, xs), [xs[0], xs[1] + 1], pts, rand)
     assert acc.verify() is False
+
+
+def test_lazy_folding_identities():
+    """The algebra behind the prover's lazy schedule (csrc/engine.cu, `lazy`): two folds of a base
+    vector (innerproductargument.go:155-166, samemultiscalarargument.go:129-135: V <- V_L + x V_R) are the linear
+    combination V2[i] = V[i] + x1 V[i + n/2] + x2 V[i + n/4] + x1 x2 V[i + 3n/4]; the second round's MSM over the
+    once-folded bases equals an MSM with two terms per base on the unfolded ones; and G' = scale * C folds the same
+    way with the scale factors carried in the scalars."""
+    rand = Rand(11)
+    n, h, q = 16, 8, 4
+    C = rand.get_g1_affines(n)
+    x1, x2 = rand.get_fr(), rand.get_fr()
+    scale = rand.get_frs(n)
+    a = rand.get_frs(h)
+
+    def fold(V, x):
+        m = len(V) // 2
+        return [bls.g1_add(V[i], bls.g1_mul(V[m + i], x)) for i in range(m)]
+
+    R = bls.R
+    V1 = fold(C, x1)
+    V2 = fold(V1, x2)
+    for i in range(q):
+        want = bls.g1_msm_naive([C[i], C[i + h], C[i + q], C[i + 3 * q]], [1, x1, x2, x1 * x2 % R])
+        assert bls.g1_eq(V2[i], want)
+    # second-round MSM <a, V1> on pairs of unfolded bases
+    pts, scs = [], []
+    for e in range(h):
+        pts += [C[e], C[e + h]]
+        scs += [a[e], a[e] * x1 % R]
+    assert bls.g1_eq(bls.g1_msm_naive(V1, a), bls.g1_msm_naive(pts, scs))
+    # G'[i] = scale[i] C[i]: folds with the inverse challenges, scale factors multiplied into the scalars
+    y1, y2 = bls.fr_inv(x1), bls.fr_inv(x2)
+    Gp2 = fold(fold([bls.g1_mul(C[i], scale[i]) for i in range(n)], y1), y2)
+    for i in range(q):
+        want = bls.g1_msm_naive([C[i], C[i + h], C[i + q], C[i + 3 * q]],
+                                [scale[i], y1 * scale[i + h] % R, y2 * scale[i + q] % R, y1 * y2 % R * scale[i + 3 * q] % R])
+        assert bls.g1_eq(Gp2[i], want)
