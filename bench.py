@@ -713,6 +713,8 @@ def gpu_main(args):
                            "kind 0) / 300 per modmul",
             "avg_launch_ms": tk["ms"] / n_launch, "launches": tk["launches"],
             "algorithmic_modmul_per_launch": tk["modmul"] / n_launch,
+            "work_definition": "SURVEY.md 8d modmul(N) per MSM task at the REFERENCE's term count N (a base the prover "
+                               "writes as several CRS-point terms counts once), summed over the tasks of a launch",
             "hbm": {"achieved_gbs": tk["bytes"] / (tk["ms"] * 1e-3) / 1e9 if tk["ms"] else 0.0, "peak_gbs": hbm_peak,
                     "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
             "per_kernel": {k: {"ms": v["ms"], "launches": v["launches"],
